@@ -1,0 +1,20 @@
+// k1_fused.h -- launcher of the fused pull-stream + moments + equilibrium + collision kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include "lbm_consts.h"
+
+namespace plbm {
+
+// The 12 moment fields LBmethod hands to visualize::UpdateVisualization
+// (/root/reference/src/plasma.cpp:516-522); rho_q, Ex, Ey live in their own buffers.
+struct MacroOut {
+    double* ux[3];
+    double* uy[3];
+    double* T[3];
+    double* rho[3];
+};
+
+cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,
+                            const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
+
+} // namespace plbm

@@ -1,0 +1,190 @@
+// lbm_cell.cuh -- per-cell arithmetic of the three-species plasma LBM step, written once and used
+// by the fused kernel (k1_fused.cu) and by the per-phase kernels behind the reference's free
+// functions (phases.cu).
+//
+// Every function states the reference expression it evaluates (file:line under /root/reference)
+// and, where the evaluation is reorganised, why the result is bit-identical:
+//   (E1) products with the lattice velocities c in {0,+1,-1} are exact, x + (+-0) = x, and
+//        x + (-y) = x - y, so the direction sums drop their zero terms;
+//   (E2) negation commutes with every rounded operation, so opposite directions share |c.u| work;
+//   (E3) scaling by a power of two commutes with rounding (no overflow/underflow involved), so
+//        the factors 2.0 and 0.5 of collisions.cpp:86-100 are folded into per-cell constants;
+//   (E4) x / tau for tau in {1,2,4} is the exact product x * (1/tau).
+// Signs of exact zeros may differ from the CPU; no non-zero value does.
+#pragma once
+#include <utility>
+#include "exact_math.cuh"
+
+namespace plbm {
+
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// x / tau for the reference's fixed relaxation times (collisions.cpp:6-7).            (E4)
+template <int TAU>
+__device__ __forceinline__ D div_tau(D x, const LbmConsts& c)
+{
+    if constexpr (TAU == 1) return x;
+    else if constexpr (TAU == 2) return x * D(0.5);
+    else if constexpr (TAU == 4) return x * D(0.25);
+    else if constexpr (TAU == 3) return cdiv(x, c.tau3);
+    else if constexpr (TAU == 5) return cdiv(x, c.tau5);
+    else { static_assert(TAU == 6, "unknown relaxation time"); return cdiv(x, c.tau6); }
+}
+
+// Sums over the nine directions in the reference's i = 0..8 order, plasma.cpp:352-372.   (E1)
+__device__ __forceinline__ D sum9(const D (&v)[9])
+{
+    return (((((((v[0] + v[1]) + v[2]) + v[3]) + v[4]) + v[5]) + v[6]) + v[7]) + v[8];
+}
+__device__ __forceinline__ D moment_x(const D (&f)[9])   // sum f_i * cx_i, cx = 0,1,0,-1,0,1,-1,-1,1
+{
+    return ((((f[1] - f[3]) + f[5]) - f[6]) - f[7]) + f[8];
+}
+__device__ __forceinline__ D moment_y(const D (&f)[9])   // sum f_i * cy_i, cy = 0,0,1,0,-1,1,1,-1,-1
+{
+    return ((((f[2] - f[4]) + f[5]) + f[6]) - f[7]) - f[8];
+}
+
+// Macroscopic state of one cell after UpdateMacro, plasma.cpp:317-456.
+struct CellMacro {
+    D rho[3], ux[3], uy[3], T[3];   // stored (thresholded) moments
+    D upx[3], upy[3];               // barycentric pair velocities u_ei, u_en, u_in
+    D rho_q;
+};
+
+// rl/mx/my/tl: the raw local sums of species 0..2.
+__device__ __forceinline__ void cell_update_macro(const D (&rl)[3], const D (&mx)[3], const D (&my)[3],
+                                                  const D (&tl)[3], D Ex, D Ey, const LbmConsts& c, CellMacro& m)
+{
+    static_for<3>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        if (rl[s] < D(1e-10)) {                                               // plasma.cpp:373-377
+            m.rho[s] = D(0.0); m.ux[s] = D(0.0); m.uy[s] = D(0.0); m.T[s] = D(0.0);
+        } else {
+            m.rho[s] = rl[s];
+            m.T[s] = tl[s];
+            if constexpr (s < 2) {                                            // plasma.cpp:380-391, 400-411
+                D vx = (mx[s] == rl[s] || mx[s] == -rl[s]) ? D(0.0) : xdiv(mx[s], rl[s]);
+                D vy = (my[s] == rl[s] || my[s] == -rl[s]) ? D(0.0) : xdiv(my[s], rl[s]);
+                m.ux[s] = vx + cdiv(D(c.hq[s]) * Ex, c.m[s]);                  // 0.5*q*Ex/m
+                m.uy[s] = vy + cdiv(D(c.hq[s]) * Ey, c.m[s]);
+            } else {                                                          // plasma.cpp:420-424
+                m.ux[s] = xdiv(mx[s], rl[s]);
+                m.uy[s] = xdiv(my[s], rl[s]);
+            }
+        }
+    });
+    static_for<3>([&](auto P) {                                               // plasma.cpp:426-449
+        constexpr int p = decltype(P)::value;
+        constexpr int a = (p == 2) ? 1 : 0, b = (p == 0) ? 1 : 2;
+        if (rl[a] < D(1e-10) && rl[b] < D(1e-10)) {
+            m.upx[p] = D(0.0); m.upy[p] = D(0.0);
+        } else {
+            const D den = rl[a] + rl[b];
+            m.upx[p] = xdiv(rl[a] * m.ux[a] + rl[b] * m.ux[b], den);
+            m.upy[p] = xdiv(rl[a] * m.uy[a] + rl[b] * m.uy[b], den);
+        }
+    });
+    D rq = cdiv(D(c.q[1]) * m.rho[1], c.m[1]) + cdiv(D(c.q[0]) * m.rho[0], c.m[0]);   // plasma.cpp:452
+    if (rq < D(1e-15)) rq = D(0.0);                                                    // plasma.cpp:453
+    m.rho_q = rq;
+}
+
+// Direction-independent pieces of the equilibrium bracket for one velocity (plasma.cpp:169-174,
+// 196-200):  K = u2*0.5*invcs2.
+struct VelSet {
+    D vx, vy, K;
+};
+__device__ __forceinline__ VelSet make_velset(D vx, D vy, const LbmConsts& c)
+{
+    VelSet v;
+    v.vx = vx; v.vy = vy;
+    v.K = (vx * vx + vy * vy) * D(c.hinvcs2);                                 // (u2*0.5)*invcs2        (E3)
+    return v;
+}
+
+// |c_i . u| for the four direction axes: 0: (1,0)/( -1,0), 1: (0,1)/(0,-1), 2: (1,1)/(-1,-1),
+// 3: (-1,1)/(1,-1).  The first direction of each pair has c.u = +value.                       (E1,E2)
+template <int AXIS>
+__device__ __forceinline__ D axis_dot(D vx, D vy)
+{
+    if constexpr (AXIS == 0) return vx;
+    else if constexpr (AXIS == 1) return vy;
+    else if constexpr (AXIS == 2) return vx + vy;
+    else return vy - vx;
+}
+
+// Bracket 1 + cu*invcs2 + cu*cu*0.5*invcs2*invcs2 - K for cu = +c and cu = -c, plasma.cpp:196-200.
+__device__ __forceinline__ void eq_brackets(D cu, D K, const LbmConsts& c, D& bplus, D& bminus)
+{
+    const D P = cu * D(c.invcs2);
+    const D S = ((cu * cu) * D(c.hinvcs2)) * D(c.invcs2);                    // (E3)
+    bplus = ((D(1.0) + P) + S) - K;
+    bminus = ((D(1.0) - P) + S) - K;                                         // (E2)
+}
+__device__ __forceinline__ D eq_bracket_rest(D K) { return D(1.0) - K; }     // cu = 0
+
+// Per-cell, direction-independent part of the thermal source, collisions.cpp:86-96:
+// AB2 = 2*(2*rho*a*a - 2*a*rho) for the three relaxation times of species s.            (E3)
+template <int S>
+__device__ __forceinline__ void thermal_cell_terms(D rho, const LbmConsts& c, D (&AB2)[3])
+{
+    const D r2 = D(2.0) * rho;
+    static_for<3>([&](auto M) {
+        constexpr int slot = TAU_SLOT[S][decltype(M)::value];
+        const D A = (r2 * D(c.a[slot])) * D(c.a[slot]);
+        const D B = D(c.a2[slot]) * rho;
+        AB2[decltype(M)::value] = D(2.0) * (A - B);
+    });
+}
+
+// One species, one direction: thermal collision (collisions.cpp:86-114) and mass collision
+// (collisions.cpp:154-173) given the three equilibrium brackets b[0..2] (self, pair 1, pair 2).
+//   wr = w_i*rho_s, wT = w_i*T_s, rhoh = 0.5*rho_s, u2 = ux_s^2+uy_s^2, force = Guo term (0 for neutrals)
+template <int S>
+__device__ __forceinline__ void collide_species_dir(D fv, D gv, const D (&b)[3], D wr, D wT, const D (&AB2)[3],
+                                                    D rhoh, D u2, D force, const LbmConsts& c, D& fnew, D& gnew)
+{
+    D feq[3], geq[3], q[3], df[3], dg[3];
+    static_for<3>([&](auto M) {
+        constexpr int m = decltype(M)::value;
+        constexpr int slot = TAU_SLOT[S][m];
+        constexpr int tau = TAU_VALUE[slot];
+        feq[m] = wr * b[m];                                                   // plasma.cpp:195-249
+        geq[m] = wT * b[m];                                                   // plasma.cpp:251-304
+        const D C18 = div_tau<tau>(D(18.0) * feq[m], c);                      // 2 * (Q*feq/tau)          (E3)
+        q[m] = xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                       // 2 * term_xy, collisions.cpp:86-96
+        df[m] = div_tau<tau>(fv - feq[m], c);                                 // collisions.cpp:166-168
+        dg[m] = div_tau<tau>(gv - geq[m], c);                                 // collisions.cpp:107-109
+    });
+    const D dE = (rhoh * ((q[0] + q[1]) + q[2])) * u2;                        // collisions.cpp:98-100    (E3)
+    const D dT = cdiv(dE, c.Kb);                                              // -DeltaT, collisions.cpp:102-104
+    gnew = (gv - ((dg[0] + dg[1]) + dg[2])) - dT;                             // collisions.cpp:112-114
+    fnew = fv - ((df[0] + df[1]) + df[2]);                                    // collisions.cpp:171-173
+    if constexpr (S < 2) fnew = fnew + force;
+}
+
+// Guo forcing prefactor w*q*rho/m/cs2*(1-1/(2 tau)), collisions.cpp:154,159.
+template <int S>
+__device__ __forceinline__ D guo_prefactor(int wclass, D rho, const LbmConsts& c)
+{
+    return cdiv(cdiv(D(c.wq[S][wclass]) * rho, c.m[S]), c.cs2) * D(c.gfac[S]);
+}
+// Guo bracket (c.E) + (c.u)(c.E)/cs2 - (u.E) for c and -c, collisions.cpp:155-157.             (E2)
+__device__ __forceinline__ void guo_brackets(D cu, D cE, D uE, const LbmConsts& c, D& gplus, D& gminus)
+{
+    const D X = cdiv(cu * cE, c.cs2);
+    gplus = (cE + X) - uE;
+    gminus = (X - cE) - uE;
+}
+
+} // namespace plbm

@@ -1,0 +1,423 @@
+// plbm_api.cu -- the C ABI of include/plbm.h: context, device state, and the time-step driver.
+//
+// Host-side mirror of LBmethod's constructor and loop (reference src/plasma.cpp:22-124, 459-529):
+// the context owns all state in HBM; a step is K1 (fused pull-stream/moments/equilibria/collisions)
+// followed by the Poisson solve of the configured type, exactly in the reference's order.
+#include "../../include/plbm.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "exact_math.cuh"
+#include "host_tables.h"
+#include "k1_fused.h"
+#include "layout.h"
+#include "lbm_consts.h"
+#include "poisson_fft.h"
+
+using namespace plbm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+__global__ void recip_kernel(const double* d, double* y, int n)
+{
+    const int t = threadIdx.x;
+    if (t < n) y[t] = recip_refined(d[t]);
+}
+
+} // namespace
+
+struct plbm_ctx {
+    plbm_config cfg;
+    LbmConsts consts;
+    LbmGeom geom;
+    cudaStream_t stream = nullptr;
+    double* pop[2] = { nullptr, nullptr };   // ping-pong population planes
+    int cur = 0;                             // pop[cur] holds the current post-collision state
+    double* Ex = nullptr; double* Ey = nullptr; double* rho_q = nullptr; double* phi = nullptr;
+    double* macro[12] = {};                  // ux,uy (e,i,n), T (e,i,n), rho (e,i,n) in plbm.h field order
+    double* staging = nullptr;               // 9*NX*NYl doubles for AoS transfers
+    bool macro_valid = false;
+    bool poisson_called = false;             // call_once of reference src/poisson.cpp:34-41
+    // spectral Poisson
+    PoissonFftDev fft = {};
+    cpx* tw_row = nullptr; cpx* tw_col = nullptr; double* sx2 = nullptr; double* sy2 = nullptr;
+    long long bytes = 0;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(plbm_ctx* c, T** p, size_t count)
+{
+    CUDA_TRY(cudaMalloc((void**)p, sizeof(T) * count));
+    c->bytes += (long long)(sizeof(T) * count);
+    return 0;
+}
+
+int build_consts(plbm_ctx* c)
+{
+    const plbm_config& cfg = c->cfg;
+    LbmConsts& k = c->consts;
+    k.invcs2 = 1.0 / cfg.cs2;                              // reference src/plasma.cpp:164
+    k.hinvcs2 = 0.5 * k.invcs2;
+    k.w[0] = 4.0 / 9.0; k.w[1] = 1.0 / 9.0; k.w[2] = 1.0 / 36.0;   // reference src/plasma.cpp:12-16
+    for (int s = 0; s < 2; ++s) {
+        k.hq[s] = 0.5 * cfg.q[s];                          // reference src/plasma.cpp:389,409
+        k.q[s] = cfg.q[s];
+        for (int wc = 0; wc < 3; ++wc) k.wq[s][wc] = k.w[wc] * cfg.q[s];   // reference src/collisions.cpp:154,159
+        k.gfac[s] = 1.0 - 1.0 / (2 * (double)TAU_VALUE[s]);
+    }
+    for (int slot = 0; slot < 6; ++slot) {
+        const double tau = (double)TAU_VALUE[slot];
+        k.a[slot] = 1.0 - 1.0 / tau;                       // reference src/collisions.cpp:86-96
+        k.a2[slot] = 2.0 * k.a[slot];
+        k.a4[slot] = 2.0 * k.a2[slot];
+    }
+    // refined reciprocals of the loop-invariant divisors, produced by the device itself
+    const double div_h[7] = { cfg.cs2, cfg.Kb, 3.0, 5.0, 6.0, cfg.m[0], cfg.m[1] };
+    double y_h[7];
+    double *d_d = nullptr, *d_y = nullptr;
+    CUDA_TRY(cudaMalloc(&d_d, sizeof(div_h)));
+    CUDA_TRY(cudaMalloc(&d_y, sizeof(y_h)));
+    CUDA_TRY(cudaMemcpyAsync(d_d, div_h, sizeof(div_h), cudaMemcpyHostToDevice, c->stream));
+    recip_kernel<<<1, 32, 0, c->stream>>>(d_d, d_y, 7);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(y_h, d_y, sizeof(y_h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(d_d); cudaFree(d_y);
+    Recip* slots[7] = { &k.cs2, &k.Kb, &k.tau3, &k.tau5, &k.tau6, &k.m[0], &k.m[1] };
+    for (int i = 0; i < 7; ++i) {
+        if (!std::isfinite(y_h[i]) || !(std::fabs(div_h[i]) > 1e-290) || !(std::fabs(div_h[i]) < 1e290))
+            return fail("divisor %d (%g) is outside the range the fast division supports", i, div_h[i]);
+        slots[i]->d = div_h[i];
+        slots[i]->y = y_h[i];
+    }
+    return 0;
+}
+
+int build_fft(plbm_ctx* c)
+{
+    const int NX = c->cfg.NX, NY = c->cfg.NY;
+    if (c->cfg.nranks != 1) return fail("spectral Poisson: multi-rank transpose is driven by the host layer (nranks=%d)", c->cfg.nranks);
+    if (NX > FFT_MAX_N || NY > FFT_MAX_N) return fail("spectral Poisson supports NX, NY <= %d (got %dx%d)", FFT_MAX_N, NX, NY);
+    const int n0 = NX, n1 = NY, nh = n1 / 2 + 1;
+    std::vector<double> tw((size_t)2 * (n0 > n1 ? n0 : n1));
+    if (dev_alloc(c, &c->tw_row, n1)) return 1;
+    host_twiddles(n1, tw.data());
+    CUDA_TRY(cudaMemcpy(c->tw_row, tw.data(), sizeof(cpx) * n1, cudaMemcpyHostToDevice));
+    if (dev_alloc(c, &c->tw_col, n0)) return 1;
+    host_twiddles(n0, tw.data());
+    CUDA_TRY(cudaMemcpy(c->tw_col, tw.data(), sizeof(cpx) * n0, cudaMemcpyHostToDevice));
+    std::vector<double> s2((size_t)(n0 > nh ? n0 : nh));
+    if (dev_alloc(c, &c->sx2, n0)) return 1;
+    host_sin2_rows(NX, s2.data());
+    CUDA_TRY(cudaMemcpy(c->sx2, s2.data(), sizeof(double) * n0, cudaMemcpyHostToDevice));
+    if (dev_alloc(c, &c->sy2, nh)) return 1;
+    host_sin2_cols(NY, s2.data());
+    CUDA_TRY(cudaMemcpy(c->sy2, s2.data(), sizeof(double) * nh, cudaMemcpyHostToDevice));
+    if (dev_alloc(c, &c->fft.T, (size_t)nh * n0)) return 1;
+    c->fft.n0 = n0; c->fft.n1 = n1;
+    c->fft.row.n = n1; c->fft.row.nstages = host_factorize(n1, c->fft.row.radix); c->fft.row.tw = c->tw_row;
+    c->fft.col.n = n0; c->fft.col.nstages = host_factorize(n0, c->fft.col.radix); c->fft.col.tw = c->tw_col;
+    c->fft.sx2 = c->sx2; c->fft.sy2 = c->sy2;
+    c->fft.norm = 1.0 / (NX * NY);                         // reference src/poisson.cpp:415
+    CUDA_TRY(poisson_fft_configure());
+    return 0;
+}
+
+// poisson::SolvePoisson dispatch, reference src/poisson.cpp:25-82
+int solve_poisson(plbm_ctx* c, long long* launches)
+{
+    const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
+    const int type = c->cfg.poisson_type, bc = c->cfg.bc_type;
+    if (!c->poisson_called) {
+        c->poisson_called = true;
+        CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
+        if (type == PLBM_POISSON_NONE) {
+            CUDA_TRY(cudaMemsetAsync(c->Ex, 0, sizeof(double) * n, c->stream));
+            CUDA_TRY(cudaMemsetAsync(c->Ey, 0, sizeof(double) * n, c->stream));
+        }
+    }
+    if (type == PLBM_POISSON_NONE) return 0;
+    if (bc == PLBM_BC_PERIODIC && type == PLBM_POISSON_FFT) {
+        CUDA_TRY(launch_poisson_fft(c->fft, c->rho_q, c->phi, c->stream));
+        CUDA_TRY(launch_efield_periodic(c->phi, c->Ex, c->Ey, c->cfg.NX, c->cfg.NY, c->stream));
+        if (launches) *launches += 4;
+        return 0;
+    }
+    if (bc != PLBM_BC_PERIODIC && type == PLBM_POISSON_FFT) return 0;   // reference src/poisson.cpp:76-77
+    return fail("Poisson type %d is not built yet in this library", type);
+}
+
+int one_step(plbm_ctx* c, bool want_fields, long long* launches)
+{
+    MacroOut mo;
+    for (int s = 0; s < 3; ++s) {
+        mo.ux[s] = c->macro[2 * s]; mo.uy[s] = c->macro[2 * s + 1];
+        mo.T[s] = c->macro[6 + s]; mo.rho[s] = c->macro[9 + s];
+    }
+    CUDA_TRY(launch_k1_fused(c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->rho_q, want_fields ? &mo : nullptr,
+                             c->consts, c->geom, c->stream));
+    if (launches) *launches += 1;
+    c->cur ^= 1;
+    c->macro_valid = want_fields;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* plbm_last_error(void) { return g_err.c_str(); }
+
+int plbm_units_from_si(int Z_ion, int A_ion, double Ex_SI, double Ey_SI, double T_e_SI, double T_i_SI, double T_n_SI,
+                       double n_e_SI, double n_n_SI, plbm_config* o)
+{
+    if (!o) return fail("plbm_units_from_si: null config");
+    // reference include/plasma.hpp:76-133, same expression order
+    const double kB_SI = 1.380649e-23, e_charge_SI = 1.602176634e-19, epsilon0_SI = 8.854187817e-12;
+    const double m_e_SI = 9.10938356e-31, u_SI = 1.66053906660e-27;
+    const double m_i_SI = A_ion * u_SI, m_n_SI = A_ion * u_SI;
+    const double n0_SI = n_e_SI, M0_SI = m_e_SI, T0_SI = T_e_SI, Q0_SI = e_charge_SI;
+    const double L0_SI = std::sqrt(epsilon0_SI * kB_SI * T0_SI / (n0_SI * Q0_SI * Q0_SI)) * 1e-2;
+    const double t0_SI = std::sqrt(epsilon0_SI * M0_SI / (3.0 * n0_SI * Q0_SI * Q0_SI)) * 1e-2;
+    const double E0_SI = M0_SI * L0_SI / (Q0_SI * t0_SI * t0_SI);
+    o->cs2 = kB_SI * T0_SI / M0_SI * t0_SI * t0_SI / (L0_SI * L0_SI);
+    o->Kb = kB_SI * (t0_SI * t0_SI * T0_SI) / (L0_SI * L0_SI * M0_SI);
+    o->Ex_ext = Ex_SI / E0_SI;
+    o->Ey_ext = Ey_SI / E0_SI;
+    o->T_init[0] = T_e_SI / T0_SI; o->T_init[1] = T_i_SI / T0_SI; o->T_init[2] = T_n_SI / T0_SI;
+    o->m[0] = m_e_SI / M0_SI; o->m[1] = m_i_SI / M0_SI; o->m[2] = m_n_SI / M0_SI;
+    o->q[0] = -e_charge_SI / Q0_SI; o->q[1] = Z_ion * e_charge_SI / Q0_SI; o->q[2] = 0.0;
+    o->rho_init[0] = o->m[0] * n_e_SI / n0_SI;
+    o->rho_init[1] = o->m[1] * n_e_SI / n0_SI / Z_ion;
+    o->rho_init[2] = o->m[2] * n_n_SI / n0_SI;
+    return 0;
+}
+
+int plbm_create(const plbm_config* cfg, plbm_ctx** out)
+{
+    if (!cfg || !out) return fail("plbm_create: null argument");
+    *out = nullptr;
+    if (cfg->NX < 3 || cfg->NY < 3) return fail("plbm_create: lattice %dx%d too small", cfg->NX, cfg->NY);
+    if ((long long)cfg->NX * cfg->NY * 9 >= (1LL << 31))
+        return fail("plbm_create: NX*NY*9 must stay below 2^31 like the reference's int indices (reference src/plasma.cpp:58)");
+    if (cfg->poisson_type < 0 || cfg->poisson_type > 4) return fail("plbm_create: unknown Poisson type %d", cfg->poisson_type);
+    if (cfg->bc_type != PLBM_BC_PERIODIC) return fail("plbm_create: boundary type %d is not built yet", cfg->bc_type);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("plbm_create: no CUDA device (this library has no CPU path)");
+    if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
+
+    plbm_ctx* c = new plbm_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.nranks <= 1) { c->cfg.nranks = 1; c->cfg.rank = 0; c->cfg.y0 = 0; c->cfg.NY_local = cfg->NY; }
+    if (c->cfg.y0 < 0 || c->cfg.NY_local < 1 || c->cfg.y0 + c->cfg.NY_local > cfg->NY) {
+        delete c;
+        return fail("plbm_create: slab [%d, %d) outside the lattice", cfg->y0, cfg->y0 + cfg->NY_local);
+    }
+    c->geom.NX = cfg->NX;
+    c->geom.NYl = c->cfg.NY_local;
+    c->geom.pitch = ((cfg->NX + 15) / 16) * 16;
+    c->geom.plane = (long long)c->geom.pitch * (c->geom.NYl + 2);
+    c->geom.wrap_y = (c->cfg.nranks == 1) ? 1 : 0;
+    if (c->geom.plane >= (1LL << 31)) { delete c; return fail("plbm_create: slab too large for 32-bit plane offsets"); }
+
+#define TRY_OR_DESTROY(expr) do { if ((expr) != 0) { std::string keep = g_err; plbm_destroy(c); g_err = keep; return 1; } } while (0)
+#define CUDA_OR_DESTROY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail("%s failed: %s", #expr, cudaGetErrorString(e__)); std::string keep = g_err; plbm_destroy(c); g_err = keep; return 1; } } while (0)
+    CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t n = (size_t)cfg->NX * c->geom.NYl;
+    const size_t pop_count = (size_t)NPLANES * c->geom.plane;
+    for (int b = 0; b < 2; ++b) {
+        TRY_OR_DESTROY(dev_alloc(c, &c->pop[b], pop_count));
+        CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
+    }
+    TRY_OR_DESTROY(dev_alloc(c, &c->Ex, n));
+    TRY_OR_DESTROY(dev_alloc(c, &c->Ey, n));
+    TRY_OR_DESTROY(dev_alloc(c, &c->rho_q, n));
+    TRY_OR_DESTROY(dev_alloc(c, &c->phi, n));
+    for (int k = 0; k < 12; ++k) TRY_OR_DESTROY(dev_alloc(c, &c->macro[k], n));
+    TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
+    CUDA_OR_DESTROY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
+    CUDA_OR_DESTROY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
+    CUDA_OR_DESTROY(launch_fill(c->Ex, cfg->Ex_ext, n, c->stream));        // reference src/plasma.cpp:116-117
+    CUDA_OR_DESTROY(launch_fill(c->Ey, cfg->Ey_ext, n, c->stream));
+    TRY_OR_DESTROY(build_consts(c));
+    if (cfg->poisson_type == PLBM_POISSON_FFT && cfg->bc_type == PLBM_BC_PERIODIC) TRY_OR_DESTROY(build_fft(c));
+    CUDA_OR_DESTROY(cudaStreamSynchronize(c->stream));
+#undef TRY_OR_DESTROY
+#undef CUDA_OR_DESTROY
+    *out = c;
+    return 0;
+}
+
+void plbm_destroy(plbm_ctx* c)
+{
+    if (!c) return;
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto e : c->events) cudaEventDestroy(e);
+    for (int b = 0; b < 2; ++b) cudaFree(c->pop[b]);
+    cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
+    for (int k = 0; k < 12; ++k) cudaFree(c->macro[k]);
+    cudaFree(c->staging);
+    cudaFree(c->tw_row); cudaFree(c->tw_col); cudaFree(c->sx2); cudaFree(c->sy2); cudaFree(c->fft.T);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int plbm_initialize(plbm_ctx* c)
+{
+    if (!c) return fail("plbm_initialize: null context");
+    CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
+    return 0;
+}
+
+int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const g[3])
+{
+    if (!c || !f || !g) return fail("plbm_upload_state: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
+    for (int s = 0; s < 3; ++s)
+        for (int kind = 0; kind < 2; ++kind) {
+            const double* h = kind ? g[s] : f[s];
+            if (!h) return fail("plbm_upload_state: null array (species %d)", s);
+            CUDA_TRY(cudaMemcpyAsync(c->staging, h, bytes, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(launch_aos_to_soa(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+        }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
+{
+    if (!c || !f || !g) return fail("plbm_download_state: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
+    for (int s = 0; s < 3; ++s)
+        for (int kind = 0; kind < 2; ++kind) {
+            double* h = kind ? g[s] : f[s];
+            if (!h) continue;
+            CUDA_TRY(launch_soa_to_aos(c->pop[c->cur], c->staging, s, kind, c->geom, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(h, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+    return 0;
+}
+
+int plbm_set_efield(plbm_ctx* c, const double* Ex, const double* Ey)
+{
+    if (!c || !Ex || !Ey) return fail("plbm_set_efield: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
+{
+    if (!c) return fail("plbm_step: null context");
+    for (int t = 0; t < nsteps; ++t) {
+        if (one_step(c, want_fields && t == nsteps - 1, nullptr)) return 1;
+        if (solve_poisson(c, nullptr)) return 1;
+    }
+    return 0;
+}
+
+int plbm_sync(plbm_ctx* c)
+{
+    if (!c) return fail("plbm_sync: null context");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_download_fields(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
+{
+    if (!c || !out) return fail("plbm_download_fields: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    for (int k = 0; k < PLBM_NUM_FIELDS; ++k) {
+        if (!out[k]) continue;
+        const double* src;
+        if (k < 12) {
+            if (!c->macro_valid) return fail("plbm_download_fields: moment fields were not requested from the last plbm_step");
+            src = c->macro[k];
+        } else if (k == PLBM_F_RHO_Q) src = c->rho_q;
+        else if (k == PLBM_F_EX) src = c->Ex;
+        else if (k == PLBM_F_EY) src = c->Ey;
+        else src = c->phi;
+        CUDA_TRY(cudaMemcpyAsync(out[k], src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, float* ms_k1, float* ms_poisson, long long* launches)
+{
+    if (!c) return fail("plbm_step_timed: null context");
+    if (nsteps < 1 || nsteps > 100000) return fail("plbm_step_timed: nsteps out of range");
+    const size_t need = (size_t)2 * nsteps + 1;
+    while (c->events.size() < need) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->events.push_back(e);
+    }
+    long long nl = 0;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(c->events[0], c->stream));
+    for (int t = 0; t < nsteps; ++t) {
+        if (one_step(c, want_fields && t == nsteps - 1, &nl)) return 1;
+        CUDA_TRY(cudaEventRecord(c->events[2 * t + 1], c->stream));
+        if (solve_poisson(c, &nl)) return 1;
+        CUDA_TRY(cudaEventRecord(c->events[2 * t + 2], c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float total = 0.f, k1 = 0.f, ps = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&total, c->events[0], c->events[2 * nsteps]));
+    for (int t = 0; t < nsteps; ++t) {
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&a, c->events[2 * t], c->events[2 * t + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, c->events[2 * t + 1], c->events[2 * t + 2]));
+        k1 += a; ps += b;
+    }
+    if (ms_total) *ms_total = total;
+    if (ms_k1) *ms_k1 = k1;
+    if (ms_poisson) *ms_poisson = ps;
+    if (launches) *launches = nl;
+    return 0;
+}
+
+int plbm_local_rows(const plbm_ctx* c, int* y0, int* ny_local)
+{
+    if (!c) return fail("plbm_local_rows: null context");
+    if (y0) *y0 = c->cfg.y0;
+    if (ny_local) *ny_local = c->geom.NYl;
+    return 0;
+}
+
+long long plbm_device_bytes(const plbm_ctx* c) { return c ? c->bytes : 0; }
+void* plbm_stream(plbm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+} // extern "C"

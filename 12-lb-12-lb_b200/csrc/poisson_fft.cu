@@ -1,0 +1,160 @@
+// poisson_fft.cu -- spectral Poisson solve and field reconstruction on the device.
+//
+//   poisson::SolvePoisson_FFT               /root/reference/src/poisson.cpp:365-420
+//   poisson::InitPoissonFFT                 /root/reference/src/poisson.cpp:611-623
+//   poisson::ComputeElectricField_Periodic  /root/reference/src/poisson.cpp:589-607
+//
+// The reference hands the flat x-fastest rho_q array to fftw_plan_dft_r2c_2d(NX, NY): n0 = NX rows
+// of n1 = NY contiguous reals (only a true 2-D transform when NX == NY; the quirk is kept).  Three
+// passes, each one CTA per sequence with the whole sequence in shared memory:
+//   P1  rows r2c   two real rows per complex transform, Hermitian split, written TRANSPOSED
+//                  T[k][r] so that P2 is contiguous (and so that slabs can be exchanged by an
+//                  all-to-all in the multi-GPU path)
+//   P2  columns    forward transform, division by the discrete-Laplacian symbol
+//                  4(sin^2(pi kx/NX) + sin^2(pi ky/NY)) (K2), inverse transform -- one kernel,
+//                  the column never leaves the SM
+//   P3  rows c2r   rebuild the packed spectrum of a row pair, inverse transform, scale by 1/(NX*NY)
+// then K3: E = -grad phi by wrapped central differences.
+// Algorithmic traffic: P1 8+8, P2 8+8, P3 8+8, K3 8+16 = 72 B per cell.
+#include "poisson_fft.h"
+#include "fft.cuh"
+
+namespace plbm {
+
+__global__ void __launch_bounds__(1024)
+poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
+                        int n0, int n1, int nh)
+{
+    extern __shared__ cpx fbuf[];
+    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const bool paired = rb < n0;
+    const double* rowa = in + (size_t)ra * n1;
+    const double* rowb = in + (size_t)rb * n1;
+    for (int j = threadIdx.x; j < n1; j += blockDim.x) {
+        cpx z;
+        z.re = __ldg(rowa + j);
+        z.im = paired ? __ldg(rowb + j) : 0.0;
+        fbuf[j] = z;
+    }
+    fft_smem<-1>(fbuf, plan);
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        const cpx Z = fbuf[k];
+        if (!paired) {
+            T[(size_t)k * n0 + ra] = Z;
+        } else {
+            const cpx Zm = fbuf[k == 0 ? 0 : n1 - k];
+            cpx A, B;
+            A.re = __dmul_rn(0.5, __dadd_rn(Z.re, Zm.re));
+            A.im = __dmul_rn(0.5, __dsub_rn(Z.im, Zm.im));
+            B.re = __dmul_rn(0.5, __dadd_rn(Z.im, Zm.im));
+            B.im = __dmul_rn(0.5, __dsub_rn(Zm.re, Z.re));
+            T[(size_t)k * n0 + ra] = A;
+            T[(size_t)k * n0 + rb] = B;
+        }
+    }
+}
+
+// One spectral column k (all kx): forward, phi_hat = rho_hat / denom (poisson.cpp:388-409), inverse.
+__global__ void __launch_bounds__(1024)
+poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
+                    const double* __restrict__ sx2, const double* __restrict__ sy2, int n0)
+{
+    extern __shared__ cpx fbuf[];
+    const int k = blockIdx.x;
+    cpx* col = T + (size_t)k * n0;
+    for (int r = threadIdx.x; r < n0; r += blockDim.x) fbuf[r] = col[r];
+    fft_smem<-1>(fbuf, plan);
+    const double syk = __ldg(sy2 + k);
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+        const double denom = __dmul_rn(4.0, __dadd_rn(__ldg(sx2 + i), syk));
+        cpx v = fbuf[i];
+        if (denom > 1e-15) {
+            v.re = xdiv(D(v.re), D(denom)).v;
+            v.im = xdiv(D(v.im), D(denom)).v;
+        } else {
+            v.re = 0.0; v.im = 0.0;
+        }
+        fbuf[i] = v;
+    }
+    fft_smem<+1>(fbuf, plan);
+    for (int r = threadIdx.x; r < n0; r += blockDim.x) col[r] = fbuf[r];
+}
+
+__global__ void __launch_bounds__(1024)
+poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, const __grid_constant__ FftPlan plan,
+                        int n0, int n1, int nh, double norm)
+{
+    extern __shared__ cpx fbuf[];
+    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const bool paired = rb < n0;
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        const cpx Ha = T[(size_t)k * n0 + ra];
+        cpx Hb = { 0.0, 0.0 };
+        if (paired) Hb = T[(size_t)k * n0 + rb];
+        const bool self_conj = (k == 0) || (2 * k == n1);      // DC / Nyquist: imaginary part ignored (c2r contract)
+        const double ar = Ha.re, ai = self_conj ? 0.0 : Ha.im;
+        const double br = Hb.re, bi = self_conj ? 0.0 : Hb.im;
+        fbuf[k] = { __dsub_rn(ar, bi), __dadd_rn(ai, br) };
+        if (!self_conj) fbuf[n1 - k] = { __dadd_rn(ar, bi), __dsub_rn(br, ai) };
+    }
+    fft_smem<+1>(fbuf, plan);
+    double* rowa = phi + (size_t)ra * n1;
+    double* rowb = phi + (size_t)rb * n1;
+    for (int j = threadIdx.x; j < n1; j += blockDim.x) {
+        const cpx z = fbuf[j];
+        rowa[j] = __dmul_rn(z.re, norm);                        // poisson.cpp:415-419
+        if (paired) rowb[j] = __dmul_rn(z.im, norm);
+    }
+}
+
+// K3, poisson.cpp:589-607
+__global__ void efield_periodic_kernel(const double* __restrict__ phi, double* __restrict__ Ex, double* __restrict__ Ey,
+                                       int NX, int NY)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= NX) return;
+    const int im1 = (i == 0) ? NX - 1 : i - 1, ip1 = (i == NX - 1) ? 0 : i + 1;
+    const int jm1 = (j == 0) ? NY - 1 : j - 1, jp1 = (j == NY - 1) ? 0 : j + 1;
+    const size_t row = (size_t)j * NX;
+    Ex[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(phi + row + ip1), __ldg(phi + row + im1)));
+    Ey[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(phi + (size_t)jp1 * NX + i), __ldg(phi + (size_t)jm1 * NX + i)));
+}
+
+static int fft_threads(int n)
+{
+    int t = (n + 7) / 8;
+    t = ((t + 31) / 32) * 32;
+    if (t < 64) t = 64;
+    if (t > 1024) t = 1024;
+    return t;
+}
+
+cudaError_t poisson_fft_configure()
+{
+    const int max_smem = (int)(sizeof(cpx) * FFT_MAX_N);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(poisson_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(poisson_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(poisson_rows_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_poisson_fft(const PoissonFftDev& p, const double* rho_q, double* phi, cudaStream_t stream)
+{
+    const int n0 = p.n0, n1 = p.n1, nh = n1 / 2 + 1;
+    const int npairs = (n0 + 1) / 2;
+    poisson_rows_fwd_kernel<<<npairs, fft_threads(n1), sizeof(cpx) * n1, stream>>>(rho_q, p.T, p.row, n0, n1, nh);
+    poisson_cols_kernel<<<nh, fft_threads(n0), sizeof(cpx) * n0, stream>>>(p.T, p.col, p.sx2, p.sy2, n0);
+    poisson_rows_inv_kernel<<<npairs, fft_threads(n1), sizeof(cpx) * n1, stream>>>(p.T, phi, p.row, n0, n1, nh, p.norm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_efield_periodic(const double* phi, double* Ex, double* Ey, int NX, int NY, cudaStream_t stream)
+{
+    dim3 grid((NX + 255) / 256, NY);
+    efield_periodic_kernel<<<grid, 256, 0, stream>>>(phi, Ex, Ey, NX, NY);
+    return cudaGetLastError();
+}
+
+} // namespace plbm

@@ -1,0 +1,107 @@
+/*
+ * plbm.h -- C ABI of the B200-native plasma lattice-Boltzmann step (libplbm.so).
+ *
+ * This is the drop-in boundary for ONE path of AMSC-24-25/12-lb-12-lb: the loop body of
+ * LBmethod::Run_simulation (reference src/plasma.cpp:476-523).  The reference has no FFI of its
+ * own (it is a single C++ program), so the boundary sits where a maintainer would cut it: under
+ * the public C++ headers.  include/plasma.hpp, collisions.hpp, streaming.hpp and poisson.hpp of
+ * this repo keep the reference's signatures and forward to the functions below; INTEGRATION.md
+ * shows the binding.  Plain pointers and sizes only; every function returns 0 on success and a
+ * non-zero code otherwise, with the text available from plbm_last_error().  There is no CPU
+ * fallback: without a CUDA device plbm_create fails.
+ *
+ * Layout contract (reference include/utils.hpp:6-11): population ("Q") arrays are
+ * i + 9*(x + NX*y), scalar fields x + NX*y, FP64 throughout.  Species order everywhere:
+ * 0 electrons, 1 ions, 2 neutrals.
+ */
+#ifndef PLBM_H
+#define PLBM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* enum values of poisson::PoissonType (reference include/poisson.hpp:15-21) */
+enum { PLBM_POISSON_NONE = 0, PLBM_POISSON_GS = 1, PLBM_POISSON_SOR = 2, PLBM_POISSON_FFT = 3, PLBM_POISSON_NPS = 4 };
+/* enum values of streaming::BCType (reference include/streaming.hpp:10-13) */
+enum { PLBM_BC_PERIODIC = 0, PLBM_BC_BOUNCEBACK = 1 };
+
+/* fields handed to visualize::UpdateVisualization (reference include/visualize.hpp:53-61), in its
+ * parameter order, followed by the potential */
+enum {
+    PLBM_F_UX_E = 0, PLBM_F_UY_E, PLBM_F_UX_I, PLBM_F_UY_I, PLBM_F_UX_N, PLBM_F_UY_N,
+    PLBM_F_T_E, PLBM_F_T_I, PLBM_F_T_N, PLBM_F_RHO_E, PLBM_F_RHO_I, PLBM_F_RHO_N,
+    PLBM_F_RHO_Q, PLBM_F_EX, PLBM_F_EY, PLBM_F_PHI, PLBM_NUM_FIELDS
+};
+
+typedef struct plbm_ctx plbm_ctx;
+
+/* Replaces the constructor arguments and in-class initialisers of LBmethod
+ * (reference include/plasma.hpp:34-49, 86-133). */
+typedef struct plbm_config {
+    int NX, NY;               /* global lattice */
+    int poisson_type;         /* PLBM_POISSON_* */
+    int bc_type;              /* PLBM_BC_* */
+    double omega_sor;
+    /* lattice-unit constants; fill with plbm_units_from_si() */
+    double cs2, Kb;
+    double Ex_ext, Ey_ext;
+    double T_init[3];
+    double m[3];
+    double q[3];
+    double rho_init[3];
+    /* y-slab decomposition: this process owns rows [y0, y0 + NY_local) of the global lattice.
+     * nranks == 1 means the whole lattice (y0 = 0, NY_local = NY). */
+    int rank, nranks;
+    int y0, NY_local;
+    int device;               /* CUDA device ordinal, -1 = current device */
+} plbm_config;
+
+const char* plbm_last_error(void);
+
+/* SI -> lattice units in the expression order of reference include/plasma.hpp:76-133.
+ * Fills cs2, Kb, E*_ext, T_init, m, q, rho_init of *cfg; leaves the other members alone. */
+int plbm_units_from_si(int Z_ion, int A_ion, double Ex_SI, double Ey_SI,
+                       double T_e_SI, double T_i_SI, double T_n_SI,
+                       double n_e_SI, double n_n_SI, plbm_config* cfg);
+
+/* LBmethod::LBmethod allocation part (reference src/plasma.cpp:58-120): device state, E = E_ext. */
+int plbm_create(const plbm_config* cfg, plbm_ctx** out);
+void plbm_destroy(plbm_ctx* ctx);
+
+/* LBmethod::Initialize (reference src/plasma.cpp:131-158), evaluated on the device. */
+int plbm_initialize(plbm_ctx* ctx);
+
+/* Populations at the top of the time loop, host AoS arrays of the LOCAL slab
+ * (9*NX*NY_local doubles each): f[3], g[3]. */
+int plbm_upload_state(plbm_ctx* ctx, const double* const f[3], const double* const g[3]);
+int plbm_download_state(plbm_ctx* ctx, double* const f[3], double* const g[3]);
+/* Electric field used by the next step (NX*NY_local doubles each). */
+int plbm_set_efield(plbm_ctx* ctx, const double* Ex, const double* Ey);
+
+/* nsteps iterations of the loop body of LBmethod::Run_simulation (reference src/plasma.cpp:476-513):
+ * UpdateMacro, ComputeEquilibrium, Collide, Stream, SolvePoisson.  With want_fields != 0 the last
+ * step also stores the 12 moment fields, so that plbm_download_fields() returns exactly what the
+ * reference passes to visualize::UpdateVisualization for that step.  Asynchronous. */
+int plbm_step(plbm_ctx* ctx, int nsteps, int want_fields);
+int plbm_sync(plbm_ctx* ctx);
+
+/* Copies the requested fields of the local slab to host memory (NX*NY_local doubles each);
+ * out[k] == NULL skips field k.  Synchronises. */
+int plbm_download_fields(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
+
+/* Same as plbm_step but timed with CUDA events on the library's stream.  Any of the outputs may
+ * be NULL.  ms_k1 / ms_poisson are the summed durations of the fused collide-stream kernel and of
+ * the Poisson + field kernels; launches = number of kernels launched. */
+int plbm_step_timed(plbm_ctx* ctx, int nsteps, int want_fields, float* ms_total, float* ms_k1, float* ms_poisson,
+                    long long* launches);
+
+/* Introspection used by the benchmarks and tests. */
+int plbm_local_rows(const plbm_ctx* ctx, int* y0, int* ny_local);
+long long plbm_device_bytes(const plbm_ctx* ctx);
+void* plbm_stream(plbm_ctx* ctx);               /* cudaStream_t the library launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

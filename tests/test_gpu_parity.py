@@ -1,0 +1,82 @@
+"""Parity of the CUDA path (through the C ABI of include/plbm.h) against the CPU checker.
+
+Bar: BIT-EXACT (up to the sign of exact zeros) for every visualised field, the potential and all
+54 populations, at every compared step -- stronger than the <= 1e-10 field-normalised tolerance
+BASELINE.json states, and the only way to hold that tolerance over hundreds of steps
+(noise-floor table).
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_fields_same, assert_same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(oracle, plbm, NX, NY, poisson, nsteps, check_steps, **kw):
+    o = oracle.PortOracle(NX, NY, poisson=poisson, **kw)
+    with plbm.PlasmaLBM(NX, NY, poisson=poisson, **kw) as sim:
+        for t in range(nsteps):
+            o.step(1)
+            want = t in check_steps
+            sim.step(1, want_fields=want)
+            if want:
+                assert_fields_same(sim.fields(), o.fields(), f"{NX}x{NY}/{poisson}/t={t}")
+        f, g = sim.download_state()
+    for s in range(3):
+        assert_same_bits(f[s], o.f(s), f"{NX}x{NY}/{poisson}: f[{s}] after {nsteps} steps")
+        assert_same_bits(g[s], o.g(s), f"{NX}x{NY}/{poisson}: g[{s}] after {nsteps} steps")
+    o.close()
+
+
+@pytest.mark.parametrize("NX,NY", [(64, 64), (50, 70), (129, 33), (16, 16)])
+def test_fused_step_without_poisson(oracle, plbm, NX, NY):
+    run_both(oracle, plbm, NX, NY, "none", 24, {0, 1, 2, 5, 23})
+
+
+@pytest.mark.parametrize("NX,NY", [(64, 64), (60, 60), (71, 71), (48, 64), (45, 30)])
+def test_fused_step_with_fft_poisson(oracle, plbm, NX, NY):
+    run_both(oracle, plbm, NX, NY, "fft", 24, {0, 1, 2, 5, 23})
+
+
+def test_reference_default_case_200x200(oracle, plbm):
+    """configs[1] of BASELINE.json: 200x200, 200 steps, FFT Poisson, periodic."""
+    run_both(oracle, plbm, 200, 200, "fft", 200, {0, 1, 10, 50, 100, 150, 199})
+
+
+def test_other_physical_parameters(oracle, plbm):
+    run_both(oracle, plbm, 40, 40, "fft", 12, {0, 11}, Z_ion=2, A_ion=4, Ex_SI=3e-2, Ey_SI=-1e-2, T_i_SI=500.0)
+
+
+def test_random_state_one_step(oracle, plbm):
+    """Arbitrary (seeded) positive populations and field: one fused step against the checker."""
+    NX, NY = 96, 40
+    rng = np.random.default_rng(1234)
+    f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9))
+    g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
+    f[1] *= 1800.0
+    f[2] *= 1e9
+    f[0][:, : NX // 3] = 0.0          # an empty electron region (threshold branch)
+    f[1][: NY // 2] *= 1e-14          # ions below the 1e-10 density threshold
+    Ex = rng.normal(0, 1e-3, size=(NY, NX))
+    Ey = rng.normal(0, 1e-3, size=(NY, NX))
+    o = oracle.PortOracle(NX, NY, poisson="none", initialize=False)
+    for s in range(3):
+        o.f(s)[...] = f[s]
+        o.g(s)[...] = g[s]
+    o.scalar(oracle.PO_EX)[...] = Ex
+    o.scalar(oracle.PO_EY)[...] = Ey
+    with plbm.PlasmaLBM(NX, NY, poisson="none", initialize=False) as sim:
+        sim.upload_state(f, g)
+        f2, g2 = sim.download_state()
+        assert_same_bits(f2, f, "upload/download round trip f")
+        assert_same_bits(g2, g, "upload/download round trip g")
+        sim.set_efield(Ex, Ey)
+        for t in range(3):
+            o.step(1)
+            sim.step(1, want_fields=True)
+            assert_fields_same(sim.fields(), o.fields(), f"random/t={t}")
+        f3, g3 = sim.download_state()
+    for s in range(3):
+        assert_same_bits(f3[s], o.f(s), f"random f[{s}]")
+        assert_same_bits(g3[s], o.g(s), f"random g[{s}]")
