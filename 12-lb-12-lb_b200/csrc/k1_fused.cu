@@ -14,8 +14,11 @@
 // Algorithmic traffic: 54*8 read + 54*8 written + Ex,Ey 16 + rho_q 8 = 888 B per cell and step.
 //
 // One thread owns one cell.  The 54 pulled populations are parked in shared memory (one column per
-// thread, conflict-free) while the moments are formed, then re-read direction by direction, which
-// keeps the register file for the ~3 k FP64 operations per cell ("K1 budget").
+// thread, conflict-free).  The cell is then processed by k1_cell<FastDiv>: moments, then a ROLLED
+// loop over the five direction axes (two opposite directions each) so that the ~2.7 k FP64
+// instructions per cell come from a loop body that fits the instruction cache.  FastDiv records
+// whether every division stayed inside the domain where its 3/9-instruction sequence is exact;
+// if not (never on physical data), the cell is recomputed out of line with IEEE divisions.
 #include "k1_fused.h"
 #include "lbm_cell.cuh"
 
@@ -23,43 +26,119 @@ namespace plbm {
 
 constexpr int K1_THREADS = 128;
 
-template <int I> struct DirInfo {
-    static constexpr int wclass = (I == 0) ? 0 : (I < 5 ? 1 : 2);
+struct K1Out {
+    double* __restrict__ dst;     // population planes, already offset to this cell
+    long long plane;
+    double* rho_q;                // already offset to this cell
+    MacroOut mo;                  // base pointers
+    long long cidx;
 };
 
-struct K1Cell {
-    CellMacro m;
-    VelSet self[3], pair[3];
-    D AB2[3][3];
-    D rhoh[3], u2[3];
-    D uE[2];
-    D Ex, Ey;
-};
-
-// collide one direction I for all species; bs/bp: equilibrium brackets for the 3 self and 3 pair velocities
-template <int I>
-__device__ __forceinline__ void k1_direction(const K1Cell& cell, const D (&bs)[3], const D (&bp)[3], const D (&guo)[2],
-                                             const D (&wr)[3], const D (&wT)[3], const D (&pref)[2],
-                                             const double* stash, double* __restrict__ dst, long long plane, long long cell_off,
-                                             const LbmConsts& c)
+template <class DV, bool WRITE_MACRO>
+__device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash, D Ex, D Ey, const K1Out& o, const LbmConsts& c)
 {
+    // ---- UpdateMacro ------------------------------------------------------------------------
+    CellMacro m;
+    {
+        D rl[3], mx[3], my[3], tl[3];
+        static_for<3>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            D f[NQ], g[NQ];
+            #pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                f[i] = D(stash[((s * 2 + 0) * NQ + i) * K1_THREADS]);
+                g[i] = D(stash[((s * 2 + 1) * NQ + i) * K1_THREADS]);
+            }
+            rl[s] = sum9(f); mx[s] = moment_x(f); my[s] = moment_y(f); tl[s] = sum9(g);
+        });
+        cell_update_macro(dv, rl, mx, my, tl, Ex, Ey, c, m);
+    }
+    *o.rho_q = m.rho_q.v;
+    if constexpr (WRITE_MACRO) {
+        static_for<3>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            o.mo.ux[s][o.cidx] = m.ux[s].v; o.mo.uy[s][o.cidx] = m.uy[s].v;
+            o.mo.T[s][o.cidx] = m.T[s].v;   o.mo.rho[s][o.cidx] = m.rho[s].v;
+        });
+    }
+
+    // ---- per-cell constants of the collision ------------------------------------------------
+    VelSet self[3], pair[3];
+    D AB2[3][3], rhoh[3], u2[3], uE[2];
     static_for<3>([&](auto S) {
         constexpr int s = decltype(S)::value;
-        constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
-        const D b[3] = { bs[s], bp[p0], bp[p1] };
-        const D fv = D(stash[((s * 2 + 0) * NQ + I) * K1_THREADS]);
-        const D gv = D(stash[((s * 2 + 1) * NQ + I) * K1_THREADS]);
-        D force = D(0.0);
-        if constexpr (s < 2) force = pref[s] * guo[s];                        // collisions.cpp:154-163
-        D fnew, gnew;
-        collide_species_dir<s>(fv, gv, b, wr[s], wT[s], cell.AB2[s], cell.rhoh[s], cell.u2[s], force, c, fnew, gnew);
-        dst[((s * 2 + 0) * NQ + I) * plane + cell_off] = fnew.v;
-        dst[((s * 2 + 1) * NQ + I) * plane + cell_off] = gnew.v;
+        self[s] = make_velset(m.ux[s], m.uy[s], c);
+        pair[s] = make_velset(m.upx[s], m.upy[s], c);
+        thermal_cell_terms<s>(m.rho[s], c, AB2[s]);
+        rhoh[s] = D(0.5) * m.rho[s];
+        u2[s] = m.ux[s] * m.ux[s] + m.uy[s] * m.uy[s];                        // collisions.cpp:98-100
     });
+    static_for<2>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        uE[s] = m.ux[s] * Ex + m.uy[s] * Ey;                                  // collisions.cpp:157,162
+    });
+
+    // ---- directions: axis 0..3 carry two opposite directions, axis 4 is the rest direction ---
+    #pragma unroll 1
+    for (int axis = 0; axis < 5; ++axis) {
+        const int wclass = (axis < 2) ? 1 : (axis < 4 ? 2 : 0);
+        D wr[3], wT[3], pref[2], X[2];
+        BracketParts ps[3], pp[3];
+        const D cE = axis_dot(axis, Ex, Ey);
+        static_for<3>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            wr[s] = D(c.w[wclass]) * m.rho[s];
+            wT[s] = D(c.w[wclass]) * m.T[s];
+            ps[s] = bracket_parts(axis_dot(axis, self[s].vx, self[s].vy), c);
+            pp[s] = bracket_parts(axis_dot(axis, pair[s].vx, pair[s].vy), c);
+        });
+        static_for<2>([&](auto S) {
+            constexpr int s = decltype(S)::value;
+            pref[s] = guo_prefactor<s>(dv, wclass, m.rho[s], c);
+            X[s] = dv.cdiv(axis_dot(axis, self[s].vx, self[s].vy) * cE, c.cs2);   // (c.u)(c.E)/cs2
+        });
+        const int nsign = (axis == 4) ? 1 : 2;
+        #pragma unroll 1
+        for (int sg = 0; sg < nsign; ++sg) {
+            const unsigned mask = sg ? 0x80000000u : 0u;
+            const int dir = (axis == 4) ? 0 : ((axis < 2 ? axis + 1 : axis + 3) + 2 * sg);
+            D bs[3], bp[3];
+            static_for<3>([&](auto S) {
+                constexpr int s = decltype(S)::value;
+                bs[s] = bracket_value(ps[s], self[s].K, mask);
+                bp[s] = bracket_value(pp[s], pair[s].K, mask);
+            });
+            const double* st = stash + dir * K1_THREADS;
+            double* out = o.dst + dir * o.plane;
+            static_for<3>([&](auto S) {
+                constexpr int s = decltype(S)::value;
+                constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
+                const D b[3] = { bs[s], bp[p0], bp[p1] };
+                const D fv = D(st[((s * 2 + 0) * NQ) * K1_THREADS]);
+                const D gv = D(st[((s * 2 + 1) * NQ) * K1_THREADS]);
+                D force = D(0.0);
+                if constexpr (s < 2) force = pref[s] * guo_bracket(X[s], cE, uE[s], mask);   // collisions.cpp:154-163
+                D fnew, gnew;
+                collide_species_dir<s>(dv, fv, gv, b, wr[s], wT[s], AB2[s], rhoh[s], u2[s], force, c, fnew, gnew);
+                dv.note_output(fnew);
+                dv.note_output(gnew);
+                out[((s * 2 + 0) * NQ) * o.plane] = fnew.v;
+                out[((s * 2 + 1) * NQ) * o.plane] = gnew.v;
+            });
+        }
+    }
+}
+
+// Out-of-line recomputation with IEEE divisions (operands outside FastDiv's proven domain).
+template <bool WRITE_MACRO>
+__device__ __noinline__ void k1_cell_exact(const double* stash, double Ex, double Ey, const K1Out* o, const LbmConsts* c)
+{
+    ExactDiv dv;
+    k1_cell<ExactDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), *o, *c);
 }
 
 template <bool WRITE_MACRO>
-__global__ void __launch_bounds__(K1_THREADS, 3)
+__global__ void __launch_bounds__(K1_THREADS, 4)
 k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 const double* __restrict__ Exf, const double* __restrict__ Eyf,
                 double* __restrict__ rho_q, const MacroOut mo,
@@ -83,103 +162,28 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
     const int r0o = (y + 1) * g.pitch, rmo = rm * g.pitch, rpo = rp * g.pitch;
     const int off[NQ] = { r0o + x, r0o + xm, rmo + x, r0o + xp, rpo + x, rmo + xm, rmo + xp, rpo + xp, rpo + xm };
 
-    K1Cell cell;
-    D rl[3], mx[3], my[3], tl[3];
-    static_for<3>([&](auto S) {
-        constexpr int s = decltype(S)::value;
-        D f[NQ], gg[NQ];
-        const double* pf = src + (long long)((s * 2 + 0) * NQ) * g.plane;
-        const double* pg = src + (long long)((s * 2 + 1) * NQ) * g.plane;
+    #pragma unroll
+    for (int sk = 0; sk < 2 * NSPEC; ++sk) {
+        const double* p = src + (long long)(sk * NQ) * g.plane;
+        double v[NQ];
         #pragma unroll
-        for (int i = 0; i < NQ; ++i) f[i] = D(__ldg(pf + i * g.plane + off[i]));
+        for (int i = 0; i < NQ; ++i) v[i] = __ldg(p + i * g.plane + off[i]);
         #pragma unroll
-        for (int i = 0; i < NQ; ++i) gg[i] = D(__ldg(pg + i * g.plane + off[i]));
-        #pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            stash[((s * 2 + 0) * NQ + i) * K1_THREADS] = f[i].v;
-            stash[((s * 2 + 1) * NQ + i) * K1_THREADS] = gg[i].v;
-        }
-        rl[s] = sum9(f); mx[s] = moment_x(f); my[s] = moment_y(f); tl[s] = sum9(gg);
-    });
-
+        for (int i = 0; i < NQ; ++i) stash[(sk * NQ + i) * K1_THREADS] = v[i];
+    }
     const long long cidx = (long long)y * g.NX + x;    // scalar fields are flat x + NX*y
-    cell.Ex = D(__ldg(Exf + cidx));
-    cell.Ey = D(__ldg(Eyf + cidx));
-    cell_update_macro(rl, mx, my, tl, cell.Ex, cell.Ey, c, cell.m);
-    rho_q[cidx] = cell.m.rho_q.v;
-    if constexpr (WRITE_MACRO) {
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            mo.ux[s][cidx] = cell.m.ux[s].v; mo.uy[s][cidx] = cell.m.uy[s].v;
-            mo.T[s][cidx] = cell.m.T[s].v;   mo.rho[s][cidx] = cell.m.rho[s].v;
-        });
-    }
+    const double Ex = __ldg(Exf + cidx), Ey = __ldg(Eyf + cidx);
 
-    static_for<3>([&](auto S) {
-        constexpr int s = decltype(S)::value;
-        cell.self[s] = make_velset(cell.m.ux[s], cell.m.uy[s], c);
-        cell.pair[s] = make_velset(cell.m.upx[s], cell.m.upy[s], c);
-        thermal_cell_terms<s>(cell.m.rho[s], c, cell.AB2[s]);
-        cell.rhoh[s] = D(0.5) * cell.m.rho[s];
-        cell.u2[s] = cell.m.ux[s] * cell.m.ux[s] + cell.m.uy[s] * cell.m.uy[s];               // collisions.cpp:98-100
-    });
-    static_for<2>([&](auto S) {
-        constexpr int s = decltype(S)::value;
-        cell.uE[s] = cell.m.ux[s] * cell.Ex + cell.m.uy[s] * cell.Ey;                         // collisions.cpp:157,162
-    });
+    K1Out o;
+    o.dst = dst + (long long)r0o + x;
+    o.plane = g.plane;
+    o.rho_q = rho_q + cidx;
+    o.mo = mo;
+    o.cidx = cidx;
 
-    const long long cell_off = (long long)r0o + x;
-
-    // ---- rest direction (weight 4/9) -------------------------------------------------------
-    {
-        D bs[3], bp[3], guo[2], wr[3], wT[3], pref[2];
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            bs[s] = eq_bracket_rest(cell.self[s].K);
-            bp[s] = eq_bracket_rest(cell.pair[s].K);
-            wr[s] = D(c.w[0]) * cell.m.rho[s];
-            wT[s] = D(c.w[0]) * cell.m.T[s];
-        });
-        static_for<2>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            pref[s] = guo_prefactor<s>(0, cell.m.rho[s], c);
-            guo[s] = D(0.0) - cell.uE[s];
-        });
-        k1_direction<0>(cell, bs, bp, guo, wr, wT, pref, stash, dst, g.plane, cell_off, c);
-    }
-    // ---- the four axes: directions (1,3), (2,4) have weight 1/9; (5,7), (6,8) weight 1/36 ----
-    static_for<2>([&](auto WC) {
-        constexpr int wclass = decltype(WC)::value + 1;
-        D wr[3], wT[3], pref[2];
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            wr[s] = D(c.w[wclass]) * cell.m.rho[s];
-            wT[s] = D(c.w[wclass]) * cell.m.T[s];
-        });
-        static_for<2>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            pref[s] = guo_prefactor<s>(wclass, cell.m.rho[s], c);
-        });
-        static_for<2>([&](auto AX) {
-            constexpr int axis = (wclass - 1) * 2 + decltype(AX)::value;
-            // first / second direction of the axis: 0:(1,3) 1:(2,4) 2:(5,7) 3:(6,8)
-            constexpr int ia = (axis == 0) ? 1 : (axis == 1) ? 2 : (axis == 2) ? 5 : 6;
-            constexpr int ib = (axis == 0) ? 3 : (axis == 1) ? 4 : (axis == 2) ? 7 : 8;
-            D bsa[3], bsb[3], bpa[3], bpb[3], ga[2], gb[2];
-            static_for<3>([&](auto S) {
-                constexpr int s = decltype(S)::value;
-                eq_brackets(axis_dot<axis>(cell.self[s].vx, cell.self[s].vy), cell.self[s].K, c, bsa[s], bsb[s]);
-                eq_brackets(axis_dot<axis>(cell.pair[s].vx, cell.pair[s].vy), cell.pair[s].K, c, bpa[s], bpb[s]);
-            });
-            const D cE = axis_dot<axis>(cell.Ex, cell.Ey);
-            static_for<2>([&](auto S) {
-                constexpr int s = decltype(S)::value;
-                guo_brackets(axis_dot<axis>(cell.self[s].vx, cell.self[s].vy), cE, cell.uE[s], c, ga[s], gb[s]);
-            });
-            k1_direction<ia>(cell, bsa, bpa, ga, wr, wT, pref, stash, dst, g.plane, cell_off, c);
-            k1_direction<ib>(cell, bsb, bpb, gb, wr, wT, pref, stash, dst, g.plane, cell_off, c);
-        });
-    });
+    FastDiv dv;
+    k1_cell<FastDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), o, c);
+    if (!dv.ok()) k1_cell_exact<WRITE_MACRO>(stash, Ex, Ey, &o, &c);
 }
 
 static constexpr size_t k1_smem_bytes() { return sizeof(double) * NPLANES * K1_THREADS; }

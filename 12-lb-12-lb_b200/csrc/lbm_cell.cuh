@@ -1,6 +1,6 @@
 // lbm_cell.cuh -- per-cell arithmetic of the three-species plasma LBM step, written once and used
 // by the fused kernel (k1_fused.cu) and by the per-phase kernels behind the reference's free
-// functions (phases.cu).
+// functions (phases.cu).  Every routine is a template on the division policy DV (exact_math.cuh).
 //
 // Every function states the reference expression it evaluates (file:line under /root/reference)
 // and, where the evaluation is reorganised, why the result is bit-identical:
@@ -29,15 +29,15 @@ __device__ __forceinline__ void static_for(F&& f)
 }
 
 // x / tau for the reference's fixed relaxation times (collisions.cpp:6-7).            (E4)
-template <int TAU>
-__device__ __forceinline__ D div_tau(D x, const LbmConsts& c)
+template <int TAU, class DV>
+__device__ __forceinline__ D div_tau(DV& dv, D x, const LbmConsts& c)
 {
     if constexpr (TAU == 1) return x;
     else if constexpr (TAU == 2) return x * D(0.5);
     else if constexpr (TAU == 4) return x * D(0.25);
-    else if constexpr (TAU == 3) return cdiv(x, c.tau3);
-    else if constexpr (TAU == 5) return cdiv(x, c.tau5);
-    else { static_assert(TAU == 6, "unknown relaxation time"); return cdiv(x, c.tau6); }
+    else if constexpr (TAU == 3) return dv.cdiv(x, c.tau3);
+    else if constexpr (TAU == 5) return dv.cdiv(x, c.tau5);
+    else { static_assert(TAU == 6, "unknown relaxation time"); return dv.cdiv(x, c.tau6); }
 }
 
 // Sums over the nine directions in the reference's i = 0..8 order, plasma.cpp:352-372.   (E1)
@@ -62,7 +62,8 @@ struct CellMacro {
 };
 
 // rl/mx/my/tl: the raw local sums of species 0..2.
-__device__ __forceinline__ void cell_update_macro(const D (&rl)[3], const D (&mx)[3], const D (&my)[3],
+template <class DV>
+__device__ __forceinline__ void cell_update_macro(DV& dv, const D (&rl)[3], const D (&mx)[3], const D (&my)[3],
                                                   const D (&tl)[3], D Ex, D Ey, const LbmConsts& c, CellMacro& m)
 {
     static_for<3>([&](auto S) {
@@ -73,13 +74,15 @@ __device__ __forceinline__ void cell_update_macro(const D (&rl)[3], const D (&mx
             m.rho[s] = rl[s];
             m.T[s] = tl[s];
             if constexpr (s < 2) {                                            // plasma.cpp:380-391, 400-411
-                D vx = (mx[s] == rl[s] || mx[s] == -rl[s]) ? D(0.0) : xdiv(mx[s], rl[s]);
-                D vy = (my[s] == rl[s] || my[s] == -rl[s]) ? D(0.0) : xdiv(my[s], rl[s]);
-                m.ux[s] = vx + cdiv(D(c.hq[s]) * Ex, c.m[s]);                  // 0.5*q*Ex/m
-                m.uy[s] = vy + cdiv(D(c.hq[s]) * Ey, c.m[s]);
+                D vx = dv.xdiv(mx[s], rl[s]);
+                D vy = dv.xdiv(my[s], rl[s]);
+                if (mx[s] == rl[s] || mx[s] == -rl[s]) vx = D(0.0);
+                if (my[s] == rl[s] || my[s] == -rl[s]) vy = D(0.0);
+                m.ux[s] = vx + dv.cdiv(D(c.hq[s]) * Ex, c.m[s]);               // 0.5*q*Ex/m
+                m.uy[s] = vy + dv.cdiv(D(c.hq[s]) * Ey, c.m[s]);
             } else {                                                          // plasma.cpp:420-424
-                m.ux[s] = xdiv(mx[s], rl[s]);
-                m.uy[s] = xdiv(my[s], rl[s]);
+                m.ux[s] = dv.xdiv(mx[s], rl[s]);
+                m.uy[s] = dv.xdiv(my[s], rl[s]);
             }
         }
     });
@@ -90,12 +93,12 @@ __device__ __forceinline__ void cell_update_macro(const D (&rl)[3], const D (&mx
             m.upx[p] = D(0.0); m.upy[p] = D(0.0);
         } else {
             const D den = rl[a] + rl[b];
-            m.upx[p] = xdiv(rl[a] * m.ux[a] + rl[b] * m.ux[b], den);
-            m.upy[p] = xdiv(rl[a] * m.uy[a] + rl[b] * m.uy[b], den);
+            m.upx[p] = dv.xdiv(rl[a] * m.ux[a] + rl[b] * m.ux[b], den);
+            m.upy[p] = dv.xdiv(rl[a] * m.uy[a] + rl[b] * m.uy[b], den);
         }
     });
-    D rq = cdiv(D(c.q[1]) * m.rho[1], c.m[1]) + cdiv(D(c.q[0]) * m.rho[0], c.m[0]);   // plasma.cpp:452
-    if (rq < D(1e-15)) rq = D(0.0);                                                    // plasma.cpp:453
+    D rq = dv.cdiv(D(c.q[1]) * m.rho[1], c.m[1]) + dv.cdiv(D(c.q[0]) * m.rho[0], c.m[0]);   // plasma.cpp:452
+    if (rq < D(1e-15)) rq = D(0.0);                                                          // plasma.cpp:453
     m.rho_q = rq;
 }
 
@@ -112,26 +115,36 @@ __device__ __forceinline__ VelSet make_velset(D vx, D vy, const LbmConsts& c)
     return v;
 }
 
-// |c_i . u| for the four direction axes: 0: (1,0)/( -1,0), 1: (0,1)/(0,-1), 2: (1,1)/(-1,-1),
-// 3: (-1,1)/(1,-1).  The first direction of each pair has c.u = +value.                       (E1,E2)
-template <int AXIS>
-__device__ __forceinline__ D axis_dot(D vx, D vy)
+// c_i . v for the first direction of the axis (the second one is its negative):              (E1,E2)
+//   axis 0: dirs (1,3) c=(1,0)   1: dirs (2,4) c=(0,1)   2: dirs (5,7) c=(1,1)   3: dirs (6,8) c=(-1,1)
+//   axis 4: the rest direction, c = 0
+__device__ __forceinline__ D axis_dot(int axis, D vx, D vy)
 {
-    if constexpr (AXIS == 0) return vx;
-    else if constexpr (AXIS == 1) return vy;
-    else if constexpr (AXIS == 2) return vx + vy;
-    else return vy - vx;
+    switch (axis) {
+    case 0: return vx;
+    case 1: return vy;
+    case 2: return vx + vy;
+    case 3: return vy - vx;
+    default: return D(0.0);
+    }
 }
 
-// Bracket 1 + cu*invcs2 + cu*cu*0.5*invcs2*invcs2 - K for cu = +c and cu = -c, plasma.cpp:196-200.
-__device__ __forceinline__ void eq_brackets(D cu, D K, const LbmConsts& c, D& bplus, D& bminus)
+// Sign-independent parts of the bracket 1 + cu*invcs2 + cu*cu*0.5*invcs2*invcs2 - K, plasma.cpp:196-200
+struct BracketParts {
+    D P, S;
+};
+__device__ __forceinline__ BracketParts bracket_parts(D cu, const LbmConsts& c)
 {
-    const D P = cu * D(c.invcs2);
-    const D S = ((cu * cu) * D(c.hinvcs2)) * D(c.invcs2);                    // (E3)
-    bplus = ((D(1.0) + P) + S) - K;
-    bminus = ((D(1.0) - P) + S) - K;                                         // (E2)
+    BracketParts b;
+    b.P = cu * D(c.invcs2);
+    b.S = ((cu * cu) * D(c.hinvcs2)) * D(c.invcs2);                           // (E3)
+    return b;
 }
-__device__ __forceinline__ D eq_bracket_rest(D K) { return D(1.0) - K; }     // cu = 0
+// bracket for cu (mask 0) or -cu (mask 0x80000000)                                               (E2)
+__device__ __forceinline__ D bracket_value(const BracketParts& b, D K, unsigned mask)
+{
+    return ((D(1.0) + flip_sign(b.P, mask)) + b.S) - K;
+}
 
 // Per-cell, direction-independent part of the thermal source, collisions.cpp:86-96:
 // AB2 = 2*(2*rho*a*a - 2*a*rho) for the three relaxation times of species s.            (E3)
@@ -150,8 +163,8 @@ __device__ __forceinline__ void thermal_cell_terms(D rho, const LbmConsts& c, D 
 // One species, one direction: thermal collision (collisions.cpp:86-114) and mass collision
 // (collisions.cpp:154-173) given the three equilibrium brackets b[0..2] (self, pair 1, pair 2).
 //   wr = w_i*rho_s, wT = w_i*T_s, rhoh = 0.5*rho_s, u2 = ux_s^2+uy_s^2, force = Guo term (0 for neutrals)
-template <int S>
-__device__ __forceinline__ void collide_species_dir(D fv, D gv, const D (&b)[3], D wr, D wT, const D (&AB2)[3],
+template <int S, class DV>
+__device__ __forceinline__ void collide_species_dir(DV& dv, D fv, D gv, const D (&b)[3], D wr, D wT, const D (&AB2)[3],
                                                     D rhoh, D u2, D force, const LbmConsts& c, D& fnew, D& gnew)
 {
     D feq[3], geq[3], q[3], df[3], dg[3];
@@ -161,30 +174,29 @@ __device__ __forceinline__ void collide_species_dir(D fv, D gv, const D (&b)[3],
         constexpr int tau = TAU_VALUE[slot];
         feq[m] = wr * b[m];                                                   // plasma.cpp:195-249
         geq[m] = wT * b[m];                                                   // plasma.cpp:251-304
-        const D C18 = div_tau<tau>(D(18.0) * feq[m], c);                      // 2 * (Q*feq/tau)          (E3)
-        q[m] = xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                       // 2 * term_xy, collisions.cpp:86-96
-        df[m] = div_tau<tau>(fv - feq[m], c);                                 // collisions.cpp:166-168
-        dg[m] = div_tau<tau>(gv - geq[m], c);                                 // collisions.cpp:107-109
+        const D C18 = div_tau<tau>(dv, D(18.0) * feq[m], c);                  // 2 * (Q*feq/tau)          (E3)
+        q[m] = dv.xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                    // 2 * term_xy, collisions.cpp:86-96
+        df[m] = div_tau<tau>(dv, fv - feq[m], c);                             // collisions.cpp:166-168
+        dg[m] = div_tau<tau>(dv, gv - geq[m], c);                             // collisions.cpp:107-109
     });
     const D dE = (rhoh * ((q[0] + q[1]) + q[2])) * u2;                        // collisions.cpp:98-100    (E3)
-    const D dT = cdiv(dE, c.Kb);                                              // -DeltaT, collisions.cpp:102-104
+    const D dT = dv.cdiv(dE, c.Kb);                                           // -DeltaT, collisions.cpp:102-104
     gnew = (gv - ((dg[0] + dg[1]) + dg[2])) - dT;                             // collisions.cpp:112-114
     fnew = fv - ((df[0] + df[1]) + df[2]);                                    // collisions.cpp:171-173
     if constexpr (S < 2) fnew = fnew + force;
 }
 
 // Guo forcing prefactor w*q*rho/m/cs2*(1-1/(2 tau)), collisions.cpp:154,159.
-template <int S>
-__device__ __forceinline__ D guo_prefactor(int wclass, D rho, const LbmConsts& c)
+template <int S, class DV>
+__device__ __forceinline__ D guo_prefactor(DV& dv, int wclass, D rho, const LbmConsts& c)
 {
-    return cdiv(cdiv(D(c.wq[S][wclass]) * rho, c.m[S]), c.cs2) * D(c.gfac[S]);
+    return dv.cdiv(dv.cdiv(D(c.wq[S][wclass]) * rho, c.m[S]), c.cs2) * D(c.gfac[S]);
 }
-// Guo bracket (c.E) + (c.u)(c.E)/cs2 - (u.E) for c and -c, collisions.cpp:155-157.             (E2)
-__device__ __forceinline__ void guo_brackets(D cu, D cE, D uE, const LbmConsts& c, D& gplus, D& gminus)
+// Guo bracket (c.E) + (c.u)(c.E)/cs2 - (u.E) for c (mask 0) and -c (mask 0x80000000),
+// collisions.cpp:155-157; X = (c.u)(c.E)/cs2 is the same for both.                             (E2)
+__device__ __forceinline__ D guo_bracket(D X, D cE, D uE, unsigned mask)
 {
-    const D X = cdiv(cu * cE, c.cs2);
-    gplus = (cE + X) - uE;
-    gminus = (X - cE) - uE;
+    return (flip_sign(cE, mask) + X) - uE;
 }
 
 } // namespace plbm

@@ -112,7 +112,8 @@ int build_consts(plbm_ctx* c)
     cudaFree(d_d); cudaFree(d_y);
     Recip* slots[7] = { &k.cs2, &k.Kb, &k.tau3, &k.tau5, &k.tau6, &k.m[0], &k.m[1] };
     for (int i = 0; i < 7; ++i) {
-        if (!std::isfinite(y_h[i]) || !(std::fabs(div_h[i]) > 1e-290) || !(std::fabs(div_h[i]) < 1e290))
+        // FastDiv's domain proof (exact_math.cuh) assumes loop-invariant divisors within 2^+-40
+        if (!std::isfinite(y_h[i]) || !(std::fabs(div_h[i]) >= 0x1p-40) || !(std::fabs(div_h[i]) <= 0x1p40))
             return fail("divisor %d (%g) is outside the range the fast division supports", i, div_h[i]);
         slots[i]->d = div_h[i];
         slots[i]->y = y_h[i];

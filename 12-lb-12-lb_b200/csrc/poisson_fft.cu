@@ -69,8 +69,8 @@ poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
         const double denom = __dmul_rn(4.0, __dadd_rn(__ldg(sx2 + i), syk));
         cpx v = fbuf[i];
         if (denom > 1e-15) {
-            v.re = xdiv(D(v.re), D(denom)).v;
-            v.im = xdiv(D(v.im), D(denom)).v;
+            v.re = __ddiv_rn(v.re, denom);
+            v.im = __ddiv_rn(v.im, denom);
         } else {
             v.re = 0.0; v.im = 0.0;
         }

