@@ -33,7 +33,9 @@ class PlbmConfig(C.Structure):
 
 
 def library_path() -> Path:
-    return PKG_DIR / "libplbm.so"
+    """In-tree library; PLBM_LIBRARY selects a differently tuned build of the same sources (benchmark sweeps)."""
+    import os
+    return Path(os.environ["PLBM_LIBRARY"]) if os.environ.get("PLBM_LIBRARY") else PKG_DIR / "libplbm.so"
 
 
 def build_library(force: bool = False) -> Path:

@@ -24,7 +24,13 @@
 
 namespace plbm {
 
-constexpr int K1_THREADS = 128;
+#ifndef PLBM_K1_THREADS
+#define PLBM_K1_THREADS 128
+#endif
+#ifndef PLBM_K1_MIN_BLOCKS
+#define PLBM_K1_MIN_BLOCKS 3
+#endif
+constexpr int K1_THREADS = PLBM_K1_THREADS;
 
 struct K1Out {
     double* __restrict__ dst;     // population planes, already offset to this cell
@@ -62,71 +68,60 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
         });
     }
 
-    // ---- per-cell constants of the collision ------------------------------------------------
-    VelSet self[3], pair[3];
-    D AB2[3][3], rhoh[3], u2[3], uE[2];
+    // ---- collisions, species by species (small live state per species) -----------------------
+    // Every species needs three equilibrium velocities: its own and those of its two pairs
+    // (plasma.cpp:195-304).  Directions: axis 0..3 carry two opposite directions, axis 4 is rest.
     static_for<3>([&](auto S) {
         constexpr int s = decltype(S)::value;
-        self[s] = make_velset(m.ux[s], m.uy[s], c);
-        pair[s] = make_velset(m.upx[s], m.upy[s], c);
-        thermal_cell_terms<s>(m.rho[s], c, AB2[s]);
-        rhoh[s] = D(0.5) * m.rho[s];
-        u2[s] = m.ux[s] * m.ux[s] + m.uy[s] * m.uy[s];                        // collisions.cpp:98-100
-    });
-    static_for<2>([&](auto S) {
-        constexpr int s = decltype(S)::value;
-        uE[s] = m.ux[s] * Ex + m.uy[s] * Ey;                                  // collisions.cpp:157,162
-    });
+        constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
+        const D vx[3] = { m.ux[s], m.upx[p0], m.upx[p1] };
+        const D vy[3] = { m.uy[s], m.upy[p0], m.upy[p1] };
+        const D u2 = vx[0] * vx[0] + vy[0] * vy[0];                           // collisions.cpp:98-100
+        D K[3];                                                               // u2*0.5*invcs2, plasma.cpp:199   (E3)
+        K[0] = u2 * D(c.hinvcs2);
+        K[1] = (vx[1] * vx[1] + vy[1] * vy[1]) * D(c.hinvcs2);
+        K[2] = (vx[2] * vx[2] + vy[2] * vy[2]) * D(c.hinvcs2);
+        D AB2[3];
+        thermal_cell_terms<s>(m.rho[s], c, AB2);
+        const D rhoh = D(0.5) * m.rho[s];
+        D uE = D(0.0);
+        if constexpr (s < 2) uE = vx[0] * Ex + vy[0] * Ey;                    // collisions.cpp:157,162
 
-    // ---- directions: axis 0..3 carry two opposite directions, axis 4 is the rest direction ---
-    #pragma unroll 1
-    for (int axis = 0; axis < 5; ++axis) {
-        const int wclass = (axis < 2) ? 1 : (axis < 4 ? 2 : 0);
-        D wr[3], wT[3], pref[2], X[2];
-        BracketParts ps[3], pp[3];
-        const D cE = axis_dot(axis, Ex, Ey);
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            wr[s] = D(c.w[wclass]) * m.rho[s];
-            wT[s] = D(c.w[wclass]) * m.T[s];
-            ps[s] = bracket_parts(axis_dot(axis, self[s].vx, self[s].vy), c);
-            pp[s] = bracket_parts(axis_dot(axis, pair[s].vx, pair[s].vy), c);
-        });
-        static_for<2>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            pref[s] = guo_prefactor<s>(dv, wclass, m.rho[s], c);
-            X[s] = dv.cdiv(axis_dot(axis, self[s].vx, self[s].vy) * cE, c.cs2);   // (c.u)(c.E)/cs2
-        });
-        const int nsign = (axis == 4) ? 1 : 2;
         #pragma unroll 1
-        for (int sg = 0; sg < nsign; ++sg) {
-            const unsigned mask = sg ? 0x80000000u : 0u;
-            const int dir = (axis == 4) ? 0 : ((axis < 2 ? axis + 1 : axis + 3) + 2 * sg);
-            D bs[3], bp[3];
-            static_for<3>([&](auto S) {
-                constexpr int s = decltype(S)::value;
-                bs[s] = bracket_value(ps[s], self[s].K, mask);
-                bp[s] = bracket_value(pp[s], pair[s].K, mask);
-            });
-            const double* st = stash + dir * K1_THREADS;
-            double* out = o.dst + dir * o.plane;
-            static_for<3>([&](auto S) {
-                constexpr int s = decltype(S)::value;
-                constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
-                const D b[3] = { bs[s], bp[p0], bp[p1] };
-                const D fv = D(st[((s * 2 + 0) * NQ) * K1_THREADS]);
-                const D gv = D(st[((s * 2 + 1) * NQ) * K1_THREADS]);
+        for (int axis = 0; axis < 5; ++axis) {
+            const int wclass = (axis < 2) ? 1 : (axis < 4 ? 2 : 0);
+            const D wr = D(c.w[wclass]) * m.rho[s];
+            const D wT = D(c.w[wclass]) * m.T[s];
+            BracketParts bp[3];
+            #pragma unroll
+            for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot(axis, vx[j], vy[j]), c);
+            D pref = D(0.0), X = D(0.0), cE = D(0.0);
+            if constexpr (s < 2) {
+                cE = axis_dot(axis, Ex, Ey);
+                pref = guo_prefactor<s>(dv, wclass, m.rho[s], c);
+                X = dv.cdiv(axis_dot(axis, vx[0], vy[0]) * cE, c.cs2);         // (c.u)(c.E)/cs2
+            }
+            const int nsign = (axis == 4) ? 1 : 2;
+            #pragma unroll 1
+            for (int sg = 0; sg < nsign; ++sg) {
+                const unsigned mask = sg ? 0x80000000u : 0u;
+                const int dir = (axis == 4) ? 0 : ((axis < 2 ? axis + 1 : axis + 3) + 2 * sg);
+                D b[3];
+                #pragma unroll
+                for (int j = 0; j < 3; ++j) b[j] = bracket_value(bp[j], K[j], mask);
+                const D fv = D(stash[((s * 2 + 0) * NQ + dir) * K1_THREADS]);
+                const D gv = D(stash[((s * 2 + 1) * NQ + dir) * K1_THREADS]);
                 D force = D(0.0);
-                if constexpr (s < 2) force = pref[s] * guo_bracket(X[s], cE, uE[s], mask);   // collisions.cpp:154-163
+                if constexpr (s < 2) force = pref * guo_bracket(X, cE, uE, mask);   // collisions.cpp:154-163
                 D fnew, gnew;
-                collide_species_dir<s>(dv, fv, gv, b, wr[s], wT[s], AB2[s], rhoh[s], u2[s], force, c, fnew, gnew);
+                collide_species_dir<s>(dv, fv, gv, b, wr, wT, AB2, rhoh, u2, force, c, fnew, gnew);
                 dv.note_output(fnew);
                 dv.note_output(gnew);
-                out[((s * 2 + 0) * NQ) * o.plane] = fnew.v;
-                out[((s * 2 + 1) * NQ) * o.plane] = gnew.v;
-            });
+                o.dst[((s * 2 + 0) * NQ + dir) * o.plane] = fnew.v;
+                o.dst[((s * 2 + 1) * NQ + dir) * o.plane] = gnew.v;
+            }
         }
-    }
+    });
 }
 
 // Out-of-line recomputation with IEEE divisions (operands outside FastDiv's proven domain).
@@ -138,7 +133,7 @@ __device__ __noinline__ void k1_cell_exact(const double* stash, double Ex, doubl
 }
 
 template <bool WRITE_MACRO>
-__global__ void __launch_bounds__(K1_THREADS, 4)
+__global__ void __launch_bounds__(K1_THREADS, PLBM_K1_MIN_BLOCKS)
 k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 const double* __restrict__ Exf, const double* __restrict__ Eyf,
                 double* __restrict__ rho_q, const MacroOut mo,
