@@ -61,45 +61,68 @@ struct CellMacro {
     D rho_q;
 };
 
-// rl/mx/my/tl: the raw local sums of species 0..2.
+// Velocity of one species from its raw sums, plasma.cpp:373-424.  Returns the stored density
+// (0 below the 1e-10 threshold) and u = sum(f c)/rho (+ 0.5 q E / m for the charged species).
+template <int s, class DV>
+__device__ __forceinline__ void species_velocity(DV& dv, D rl, D mx, D my, D Ex, D Ey, const LbmConsts& c,
+                                                 D& rho, D& ux, D& uy)
+{
+    if (rl < D(1e-10)) {                                                      // plasma.cpp:373-377
+        rho = D(0.0); ux = D(0.0); uy = D(0.0);
+    } else {
+        rho = rl;
+        if constexpr (s < 2) {                                                // plasma.cpp:380-391, 400-411
+            D vx = dv.xdiv(mx, rl);
+            D vy = dv.xdiv(my, rl);
+            if (mx == rl || mx == -rl) vx = D(0.0);
+            if (my == rl || my == -rl) vy = D(0.0);
+            ux = vx + dv.cdiv(D(c.hq[s]) * Ex, c.m[s]);                        // 0.5*q*Ex/m
+            uy = vy + dv.cdiv(D(c.hq[s]) * Ey, c.m[s]);
+        } else {                                                              // plasma.cpp:420-424
+            ux = dv.xdiv(mx, rl);
+            uy = dv.xdiv(my, rl);
+        }
+    }
+}
+
+// Barycentric velocity of a pair from the raw densities and the stored velocities, plasma.cpp:426-449.
+template <class DV>
+__device__ __forceinline__ void pair_velocity(DV& dv, D rla, D rlb, D uxa, D uya, D uxb, D uyb, D& upx, D& upy)
+{
+    if (rla < D(1e-10) && rlb < D(1e-10)) {
+        upx = D(0.0); upy = D(0.0);
+    } else {
+        const D den = rla + rlb;
+        upx = dv.xdiv(rla * uxa + rlb * uxb, den);
+        upy = dv.xdiv(rla * uya + rlb * uyb, den);
+    }
+}
+
+// Charge density from the stored densities, plasma.cpp:452-453.
+template <class DV>
+__device__ __forceinline__ D charge_density(DV& dv, D rho_e, D rho_i, const LbmConsts& c)
+{
+    D rq = dv.cdiv(D(c.q[1]) * rho_i, c.m[1]) + dv.cdiv(D(c.q[0]) * rho_e, c.m[0]);
+    if (rq < D(1e-15)) rq = D(0.0);
+    return rq;
+}
+
+// rl/mx/my/tl: the raw local sums of species 0..2.  Whole UpdateMacro of one cell.
 template <class DV>
 __device__ __forceinline__ void cell_update_macro(DV& dv, const D (&rl)[3], const D (&mx)[3], const D (&my)[3],
                                                   const D (&tl)[3], D Ex, D Ey, const LbmConsts& c, CellMacro& m)
 {
     static_for<3>([&](auto S) {
         constexpr int s = decltype(S)::value;
-        if (rl[s] < D(1e-10)) {                                               // plasma.cpp:373-377
-            m.rho[s] = D(0.0); m.ux[s] = D(0.0); m.uy[s] = D(0.0); m.T[s] = D(0.0);
-        } else {
-            m.rho[s] = rl[s];
-            m.T[s] = tl[s];
-            if constexpr (s < 2) {                                            // plasma.cpp:380-391, 400-411
-                D vx = dv.xdiv(mx[s], rl[s]);
-                D vy = dv.xdiv(my[s], rl[s]);
-                if (mx[s] == rl[s] || mx[s] == -rl[s]) vx = D(0.0);
-                if (my[s] == rl[s] || my[s] == -rl[s]) vy = D(0.0);
-                m.ux[s] = vx + dv.cdiv(D(c.hq[s]) * Ex, c.m[s]);               // 0.5*q*Ex/m
-                m.uy[s] = vy + dv.cdiv(D(c.hq[s]) * Ey, c.m[s]);
-            } else {                                                          // plasma.cpp:420-424
-                m.ux[s] = dv.xdiv(mx[s], rl[s]);
-                m.uy[s] = dv.xdiv(my[s], rl[s]);
-            }
-        }
+        species_velocity<s>(dv, rl[s], mx[s], my[s], Ex, Ey, c, m.rho[s], m.ux[s], m.uy[s]);
+        m.T[s] = (rl[s] < D(1e-10)) ? D(0.0) : tl[s];
     });
-    static_for<3>([&](auto P) {                                               // plasma.cpp:426-449
+    static_for<3>([&](auto P) {
         constexpr int p = decltype(P)::value;
         constexpr int a = (p == 2) ? 1 : 0, b = (p == 0) ? 1 : 2;
-        if (rl[a] < D(1e-10) && rl[b] < D(1e-10)) {
-            m.upx[p] = D(0.0); m.upy[p] = D(0.0);
-        } else {
-            const D den = rl[a] + rl[b];
-            m.upx[p] = dv.xdiv(rl[a] * m.ux[a] + rl[b] * m.ux[b], den);
-            m.upy[p] = dv.xdiv(rl[a] * m.uy[a] + rl[b] * m.uy[b], den);
-        }
+        pair_velocity(dv, rl[a], rl[b], m.ux[a], m.uy[a], m.ux[b], m.uy[b], m.upx[p], m.upy[p]);
     });
-    D rq = dv.cdiv(D(c.q[1]) * m.rho[1], c.m[1]) + dv.cdiv(D(c.q[0]) * m.rho[0], c.m[0]);   // plasma.cpp:452
-    if (rq < D(1e-15)) rq = D(0.0);                                                          // plasma.cpp:453
-    m.rho_q = rq;
+    m.rho_q = charge_density(dv, m.rho[0], m.rho[1], c);
 }
 
 // Direction-independent pieces of the equilibrium bracket for one velocity (plasma.cpp:169-174,
