@@ -29,7 +29,8 @@ class PlbmConfig(C.Structure):
                 ("omega_sor", C.c_double), ("cs2", C.c_double), ("Kb", C.c_double),
                 ("Ex_ext", C.c_double), ("Ey_ext", C.c_double),
                 ("T_init", C.c_double * 3), ("m", C.c_double * 3), ("q", C.c_double * 3), ("rho_init", C.c_double * 3),
-                ("rank", C.c_int), ("nranks", C.c_int), ("y0", C.c_int), ("NY_local", C.c_int), ("device", C.c_int)]
+                ("rank", C.c_int), ("nranks", C.c_int), ("y0", C.c_int), ("NY_local", C.c_int), ("device", C.c_int),
+                ("fields_only", C.c_int)]
 
 
 def library_path() -> Path:

@@ -50,6 +50,8 @@ __global__ void recip_kernel(const double* d, double* y, int n)
 
 } // namespace
 
+int plbm_set_error(const char* msg) { return fail("%s", msg); }
+
 struct plbm_ctx {
     plbm_config cfg;
     LbmConsts consts;
@@ -151,32 +153,57 @@ int build_fft(plbm_ctx* c)
     return 0;
 }
 
+// call_once part of poisson::SolvePoisson, reference src/poisson.cpp:34-41
+int poisson_first_call(plbm_ctx* c)
+{
+    if (c->poisson_called) return 0;
+    c->poisson_called = true;
+    const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
+    CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
+    if (c->cfg.poisson_type == PLBM_POISSON_NONE) {
+        CUDA_TRY(cudaMemsetAsync(c->Ex, 0, sizeof(double) * n, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->Ey, 0, sizeof(double) * n, c->stream));
+    }
+    return 0;
+}
+
+// one of poisson::SolvePoisson_{GS,SOR,FFT,9point}: rho_q -> phi
+int poisson_solver(plbm_ctx* c, int type, long long* launches)
+{
+    if (type == PLBM_POISSON_FFT) {
+        if (!c->fft.T) return fail("spectral Poisson was not set up for this context (poisson_type must be FFT at creation)");
+        CUDA_TRY(launch_poisson_fft(c->fft, c->rho_q, c->phi, c->stream));
+        if (launches) *launches += 3;
+        return 0;
+    }
+    return fail("Poisson type %d is not built yet in this library", type);
+}
+
+// poisson::ComputeElectricField_Periodic / ComputeElectricField: phi -> Ex, Ey
+int poisson_efield(plbm_ctx* c, int bc, long long* launches)
+{
+    if (bc == PLBM_BC_PERIODIC) {
+        CUDA_TRY(launch_efield_periodic(c->phi, c->Ex, c->Ey, c->cfg.NX, c->cfg.NY, c->stream));
+        if (launches) *launches += 1;
+        return 0;
+    }
+    return fail("field reconstruction with walls is not built yet in this library");
+}
+
 // poisson::SolvePoisson dispatch, reference src/poisson.cpp:25-82
 int solve_poisson(plbm_ctx* c, long long* launches)
 {
-    const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
     const int type = c->cfg.poisson_type, bc = c->cfg.bc_type;
-    if (!c->poisson_called) {
-        c->poisson_called = true;
-        CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
-        if (type == PLBM_POISSON_NONE) {
-            CUDA_TRY(cudaMemsetAsync(c->Ex, 0, sizeof(double) * n, c->stream));
-            CUDA_TRY(cudaMemsetAsync(c->Ey, 0, sizeof(double) * n, c->stream));
-        }
-    }
+    if (poisson_first_call(c)) return 1;
     if (type == PLBM_POISSON_NONE) return 0;
-    if (bc == PLBM_BC_PERIODIC && type == PLBM_POISSON_FFT) {
-        CUDA_TRY(launch_poisson_fft(c->fft, c->rho_q, c->phi, c->stream));
-        CUDA_TRY(launch_efield_periodic(c->phi, c->Ex, c->Ey, c->cfg.NX, c->cfg.NY, c->stream));
-        if (launches) *launches += 4;
-        return 0;
-    }
     if (bc != PLBM_BC_PERIODIC && type == PLBM_POISSON_FFT) return 0;   // reference src/poisson.cpp:76-77
-    return fail("Poisson type %d is not built yet in this library", type);
+    if (poisson_solver(c, type, launches)) return 1;
+    return poisson_efield(c, bc, launches);
 }
 
 int one_step(plbm_ctx* c, bool want_fields, long long* launches)
 {
+    if (!c->pop[0]) return fail("plbm_step: context was created with fields_only");
     MacroOut mo;
     for (int s = 0; s < 3; ++s) {
         mo.ux[s] = c->macro[2 * s]; mo.uy[s] = c->macro[2 * s + 1];
@@ -254,7 +281,7 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)cfg->NX * c->geom.NYl;
     const size_t pop_count = (size_t)NPLANES * c->geom.plane;
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 2 && !cfg->fields_only; ++b) {
         TRY_OR_DESTROY(dev_alloc(c, &c->pop[b], pop_count));
         CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
     }
@@ -262,8 +289,8 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     TRY_OR_DESTROY(dev_alloc(c, &c->Ey, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->rho_q, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->phi, n));
-    for (int k = 0; k < 12; ++k) TRY_OR_DESTROY(dev_alloc(c, &c->macro[k], n));
-    TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
+    for (int k = 0; k < 12 && !cfg->fields_only; ++k) TRY_OR_DESTROY(dev_alloc(c, &c->macro[k], n));
+    if (!cfg->fields_only) TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
     CUDA_OR_DESTROY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
     CUDA_OR_DESTROY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
     CUDA_OR_DESTROY(launch_fill(c->Ex, cfg->Ex_ext, n, c->stream));        // reference src/plasma.cpp:116-117
@@ -294,6 +321,7 @@ void plbm_destroy(plbm_ctx* c)
 int plbm_initialize(plbm_ctx* c)
 {
     if (!c) return fail("plbm_initialize: null context");
+    if (!c->pop[0]) return fail("plbm_initialize: context was created with fields_only");
     CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
     return 0;
 }
@@ -301,6 +329,7 @@ int plbm_initialize(plbm_ctx* c)
 int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const g[3])
 {
     if (!c || !f || !g) return fail("plbm_upload_state: null argument");
+    if (!c->pop[0]) return fail("plbm_upload_state: context was created with fields_only");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
     for (int s = 0; s < 3; ++s)
         for (int kind = 0; kind < 2; ++kind) {
@@ -316,6 +345,7 @@ int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const
 int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
 {
     if (!c || !f || !g) return fail("plbm_download_state: null argument");
+    if (!c->pop[0]) return fail("plbm_download_state: context was created with fields_only");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
     for (int s = 0; s < 3; ++s)
         for (int kind = 0; kind < 2; ++kind) {
@@ -407,6 +437,45 @@ int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, f
     if (ms_k1) *ms_k1 = k1;
     if (ms_poisson) *ms_poisson = ps;
     if (launches) *launches = nl;
+    return 0;
+}
+
+int plbm_host_solve_poisson(plbm_ctx* c, const double* rho_q, double* Ex, double* Ey)
+{
+    if (!c || !rho_q || !Ex || !Ey) return fail("plbm_host_solve_poisson: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    CUDA_TRY(cudaMemcpyAsync(c->rho_q, rho_q, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (solve_poisson(c, nullptr)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(Ex, c->Ex, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(Ey, c->Ey, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_host_poisson_solver(plbm_ctx* c, int poisson_type, const double* rho_q)
+{
+    if (!c || !rho_q) return fail("plbm_host_poisson_solver: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    if (poisson_first_call(c)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->rho_q, rho_q, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (poisson_solver(c, poisson_type, nullptr)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_host_efield(plbm_ctx* c, int bc_type, double* Ex, double* Ey)
+{
+    if (!c || !Ex || !Ey) return fail("plbm_host_efield: null argument");
+    const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    if (poisson_first_call(c)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (poisson_efield(c, bc_type, nullptr)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(Ex, c->Ex, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(Ey, c->Ey, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

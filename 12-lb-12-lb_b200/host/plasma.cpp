@@ -1,0 +1,78 @@
+// plasma.cpp -- LBmethod over the C ABI of include/plbm.h.
+// Mirrors the reference's constructor + Run_simulation (src/plasma.cpp:22-124, 459-529); the loop
+// body itself (UpdateMacro, ComputeEquilibrium, Collide, Stream, SolvePoisson) runs on the device.
+#include "plasma.hpp"
+#include "plbm.h"
+
+#include <iostream>
+#include <stdexcept>
+#include <string>
+
+namespace {
+[[noreturn]] void raise(const char* what)
+{
+    throw std::runtime_error(std::string(what) + ": " + plbm_last_error());
+}
+}
+
+LBmethod::LBmethod(const int _NSTEPS, const int _NX, const int _NY, const size_t _n_cores,
+                   const int Z_ion, const int A_ion, const double Ex_SI, const double Ey_SI,
+                   const double T_e_SI_init, const double T_i_SI_init, const double T_n_SI_init,
+                   const double n_e_SI_init, const double n_n_SI_init,
+                   const poisson::PoissonType poisson_type, const streaming::BCType bc_type, const double omega_sor)
+    : NSTEPS(_NSTEPS), NX(_NX), NY(_NY), n_cores(_n_cores)
+{
+    plbm_config cfg = {};
+    cfg.NX = NX; cfg.NY = NY;
+    cfg.poisson_type = static_cast<int>(poisson_type);     // same enumerator order as the reference
+    cfg.bc_type = static_cast<int>(bc_type);
+    cfg.omega_sor = omega_sor;
+    cfg.rank = 0; cfg.nranks = 1; cfg.y0 = 0; cfg.NY_local = NY; cfg.device = -1;
+    if (plbm_units_from_si(Z_ion, A_ion, Ex_SI, Ey_SI, T_e_SI_init, T_i_SI_init, T_n_SI_init, n_e_SI_init, n_n_SI_init, &cfg))
+        raise("LBmethod: unit conversion");
+    if (plbm_create(&cfg, &ctx_)) raise("LBmethod: device state");
+    if (plbm_initialize(ctx_)) { plbm_destroy(ctx_); ctx_ = nullptr; raise("LBmethod: Initialize"); }
+    const size_t n = static_cast<size_t>(NX) * NY;
+    for (auto& f : fields_) f.assign(n, 0.0);
+}
+
+LBmethod::~LBmethod() { plbm_destroy(ctx_); }
+
+void LBmethod::fetch_fields()
+{
+    double* out[PLBM_NUM_FIELDS] = {};
+    for (int k = 0; k < 15; ++k) out[k] = fields_[k].data();
+    if (plbm_download_fields(ctx_, out)) raise("LBmethod: field download");
+}
+
+void LBmethod::FetchPotential(std::vector<double>& phi) const
+{
+    phi.resize(static_cast<size_t>(NX) * NY);
+    double* out[PLBM_NUM_FIELDS] = {};
+    out[PLBM_F_PHI] = phi.data();
+    if (plbm_download_fields(ctx_, out)) raise("LBmethod: potential download");
+}
+
+void LBmethod::Step(int nsteps, bool want_fields)
+{
+    if (plbm_step(ctx_, nsteps, want_fields ? 1 : 0)) raise("LBmethod: time step");
+    if (want_fields) fetch_fields();
+    else if (plbm_sync(ctx_)) raise("LBmethod: sync");
+}
+
+void LBmethod::Run_simulation()
+{
+    visualize::InitVisualization(NX, NY, NSTEPS);
+    for (int t = 0; t < NSTEPS; ++t) {
+        Step(1, true);
+        visualize::UpdateVisualization(t, NX, NY,
+                                       fields_[PLBM_F_UX_E], fields_[PLBM_F_UY_E],
+                                       fields_[PLBM_F_UX_I], fields_[PLBM_F_UY_I],
+                                       fields_[PLBM_F_UX_N], fields_[PLBM_F_UY_N],
+                                       fields_[PLBM_F_T_E], fields_[PLBM_F_T_I], fields_[PLBM_F_T_N],
+                                       fields_[PLBM_F_RHO_E], fields_[PLBM_F_RHO_I], fields_[PLBM_F_RHO_N],
+                                       fields_[PLBM_F_RHO_Q], fields_[PLBM_F_EX], fields_[PLBM_F_EY]);
+    }
+    visualize::CloseVisualization();
+    std::cout << "Simulation ended " << std::endl;
+}

@@ -1,0 +1,53 @@
+// plasma.hpp -- class LBmethod with the reference's public surface (reference
+// include/plasma.hpp:18-52): the 16-argument constructor taking SI parameters and
+// Run_simulation().  src/main_plasma.cpp of the reference compiles against this header unchanged.
+//
+// Unlike the reference, the object owns no lattice-sized host state besides the 15 fields it
+// hands to the visualiser: populations, moments, potential and field live in B200 HBM inside a
+// plbm_ctx (include/plbm.h), and one time step is the fused kernel + Poisson solve of libplbm.so.
+#pragma once
+
+#include "collisions.hpp"
+#include "poisson.hpp"
+#include "streaming.hpp"
+#include "utils.hpp"
+#include "visualize.hpp"
+
+#include <array>
+#include <cstddef>
+#include <vector>
+
+struct plbm_ctx;
+
+class LBmethod {
+public:
+    // Same parameter list as the reference (include/plasma.hpp:34-49).  n_cores is accepted and
+    // ignored: there is no OpenMP path.  Throws std::runtime_error when no CUDA device is present
+    // or the configuration is not available on the device.
+    LBmethod(const int NSTEPS, const int NX, const int NY, const size_t n_cores,
+             const int Z_ion, const int A_ion,
+             const double Ex_SI, const double Ey_SI,
+             const double T_e_SI_init, const double T_i_SI_init, const double T_n_SI_init,
+             const double n_e_SI_init, const double n_n_SI_init,
+             const poisson::PoissonType poisson_type, const streaming::BCType bc_type,
+             const double omega_sor);
+    ~LBmethod();
+    LBmethod(const LBmethod&) = delete;
+    LBmethod& operator=(const LBmethod&) = delete;
+
+    // The complete time loop of the reference (src/plasma.cpp:459-529): per step advance the
+    // lattice on the device, copy the 15 visualised fields to the host, call the visualiser.
+    void Run_simulation();
+
+    // ---- additions (not in the reference) used by benchmarks and tests -----------------------
+    void Step(int nsteps, bool fetch_fields);                 // nsteps of the loop body without visualisation
+    const std::vector<double>& Field(int plbm_field_id) const { return fields_[plbm_field_id]; }
+    void FetchPotential(std::vector<double>& phi) const;
+
+private:
+    const int NSTEPS, NX, NY;
+    const size_t n_cores;
+    plbm_ctx* ctx_ = nullptr;
+    std::vector<double> fields_[15];                          // order of visualize::UpdateVisualization
+    void fetch_fields();
+};

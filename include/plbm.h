@@ -55,6 +55,7 @@ typedef struct plbm_config {
     int rank, nranks;
     int y0, NY_local;
     int device;               /* CUDA device ordinal, -1 = current device */
+    int fields_only;          /* 1: no populations (a context that only serves plbm_host_solve_poisson & co.) */
 } plbm_config;
 
 const char* plbm_last_error(void);
@@ -95,6 +96,44 @@ int plbm_download_fields(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
  * the Poisson + field kernels; launches = number of kernels launched. */
 int plbm_step_timed(plbm_ctx* ctx, int nsteps, int want_fields, float* ms_total, float* ms_k1, float* ms_poisson,
                     long long* launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stateless per-phase entry points on HOST arrays in the reference layout: upload -> kernel ->
+ * download.  They back the free functions of include/collisions.hpp / streaming.hpp (semantic
+ * drop-in, not the fast path) and let tests compare single phases.  Arrays of 3 are per species;
+ * arrays of 9 equilibria are ordered  e, i, n, e_i, e_n, i_n, i_e, n_e, n_i  exactly like the
+ * parameter lists of the reference (include/collisions.hpp:10-29).
+ * ------------------------------------------------------------------------------------------- */
+/* LBmethod::UpdateMacro (reference src/plasma.cpp:317-456); upx/upy = u_e_i, u_e_n, u_i_n */
+int plbm_host_update_macro(int NX, int NY, const plbm_config* units,
+                           const double* const f[3], const double* const g[3], const double* Ex, const double* Ey,
+                           double* const rho[3], double* const ux[3], double* const uy[3], double* const T[3],
+                           double* const upx[3], double* const upy[3], double* rho_q);
+/* LBmethod::ComputeEquilibrium (reference src/plasma.cpp:162-308) */
+int plbm_host_equilibrium(int NX, int NY, const plbm_config* units,
+                          const double* const rho[3], const double* const ux[3], const double* const uy[3], const double* const T[3],
+                          const double* const upx[3], const double* const upy[3],
+                          double* const f_eq[9], double* const g_eq[9]);
+/* collisions::ThermalCollisions (reference src/collisions.cpp:64-122): out[3] receives g + C_T + DeltaT */
+int plbm_host_thermal_collisions(int NX, int NY, const plbm_config* units,
+                                 const double* const g[3], const double* const g_eq[9], const double* const f_eq[9],
+                                 const double* const rho[3], const double* const ux[3], const double* const uy[3],
+                                 double* const out[3]);
+/* collisions::Collisions (reference src/collisions.cpp:128-181): out[3] receives f + C (+ F) */
+int plbm_host_collisions(int NX, int NY, const plbm_config* units,
+                         const double* const f[3], const double* const f_eq[9],
+                         const double* const rho[3], const double* const ux[3], const double* const uy[3],
+                         const double* Ex, const double* Ey, double* const out[3]);
+/* streaming::StreamingPeriodic / ThermalStreamingPeriodic (reference src/streaming.cpp:35-59): out[3] receives the
+ * streamed populations.  bc_type other than PLBM_BC_PERIODIC: see plbm_last_error(). */
+int plbm_host_stream(int NX, int NY, int bc_type, const double* const in[3], double* const out[3]);
+/* poisson::SolvePoisson (reference src/poisson.cpp:25-82) on a context created for the lattice: rho_q in,
+ * Ex/Ey updated in place, potential kept inside the context (warm start, like the reference's static phi). */
+int plbm_host_solve_poisson(plbm_ctx* ctx, const double* rho_q, double* Ex, double* Ey);
+/* the two halves separately: poisson::SolvePoisson_{GS,SOR,FFT,9point} (rho_q -> phi, kept in the context) and
+ * poisson::ComputeElectricField[_Periodic] (phi -> Ex, Ey; Ex/Ey are in-out because walls copy onto the rim) */
+int plbm_host_poisson_solver(plbm_ctx* ctx, int poisson_type, const double* rho_q);
+int plbm_host_efield(plbm_ctx* ctx, int bc_type, double* Ex, double* Ey);
 
 /* Introspection used by the benchmarks and tests. */
 int plbm_local_rows(const plbm_ctx* ctx, int* y0, int* ny_local);

@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol(plbm):
 
 
 def test_config_struct_matches_header(plbm):
-    """Field order/types of the ctypes mirror follow the C struct (spot check by size: 5 ints+pad, 17 doubles, 5 ints)."""
-    assert C.sizeof(plbm.PlbmConfig) == 4 * 4 + 8 * 17 + 5 * 4 + 4
+    """Field order/types of the ctypes mirror follow the C struct (spot check by size: 4 ints, 17 doubles, 6 ints)."""
+    assert C.sizeof(plbm.PlbmConfig) == 4 * 4 + 8 * 17 + 6 * 4
 
 
 def test_units_match_the_reference(plbm, oracle):
