@@ -9,5 +9,7 @@ imports ``oracle/``.  (The directory name is not a Python identifier: import it 
 from .api import (PlasmaLBM, PlbmConfig, PlbmError, FIELD_NAMES, POISSON, BC, DEFAULT_SI,
                   build_library, load_library, library_path, units_from_si)
 
-__all__ = ["PlasmaLBM", "PlbmConfig", "PlbmError", "FIELD_NAMES", "POISSON", "BC", "DEFAULT_SI",
+from .distributed import CudaSlabBackend, SlabDriver, slab_of  # noqa: E402
+
+__all__ = ["CudaSlabBackend", "SlabDriver", "slab_of", "PlasmaLBM", "PlbmConfig", "PlbmError", "FIELD_NAMES", "POISSON", "BC", "DEFAULT_SI",
            "build_library", "load_library", "library_path", "units_from_si"]

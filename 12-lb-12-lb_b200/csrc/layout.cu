@@ -68,6 +68,33 @@ __global__ void initialize_kernel(double* __restrict__ planes, LbmGeom g, int NY
     }
 }
 
+// K5: boundary rows of the planes that leave the slab.  Directions with cy = +1 (2,5,6) of the top
+// local row travel to the upper neighbour, directions with cy = -1 (4,7,8) of the bottom local row
+// to the lower neighbour; 6 (species,kind) x 3 directions = 18 rows of NX doubles per side.
+__constant__ int c_dir_up[3] = { 2, 5, 6 };
+__constant__ int c_dir_down[3] = { 4, 7, 8 };
+
+__global__ void halo_pack_kernel(const double* __restrict__ planes, double* __restrict__ send_lo, double* __restrict__ send_hi, LbmGeom g)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;                 // 0..17: (species*2+kind)*3 + j
+    if (x >= g.NX) return;
+    const int sk = r / 3, j = r % 3;
+    send_hi[(size_t)r * g.NX + x] = planes[(long long)(sk * NQ + c_dir_up[j]) * g.plane + (long long)g.NYl * g.pitch + x];
+    send_lo[(size_t)r * g.NX + x] = planes[(long long)(sk * NQ + c_dir_down[j]) * g.plane + (long long)1 * g.pitch + x];
+}
+
+// what the lower neighbour sent up lands in halo row 0, what the upper neighbour sent down in row NYl+1
+__global__ void halo_unpack_kernel(double* __restrict__ planes, const double* __restrict__ recv_lo, const double* __restrict__ recv_hi, LbmGeom g)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (x >= g.NX) return;
+    const int sk = r / 3, j = r % 3;
+    planes[(long long)(sk * NQ + c_dir_up[j]) * g.plane + x] = recv_lo[(size_t)r * g.NX + x];
+    planes[(long long)(sk * NQ + c_dir_down[j]) * g.plane + (long long)(g.NYl + 1) * g.pitch + x] = recv_hi[(size_t)r * g.NX + x];
+}
+
 __global__ void fill_kernel(double* p, double v, size_t n)
 {
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) p[t] = v;
@@ -97,6 +124,18 @@ cudaError_t launch_initialize(double* planes, const LbmGeom& g, int NY, int y0,
     for (int k = 0; k < 3; ++k) { p.rho_init[k] = rho_init[k]; p.T_init[k] = T_init[k]; p.w[k] = w[k]; }
     dim3 grid((g.NX + 127) / 128, g.NYl + 2);
     initialize_kernel<<<grid, 128, 0, s>>>(planes, g, NY, y0, p);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_pack(const double* planes, double* send_lo, double* send_hi, const LbmGeom& g, cudaStream_t s)
+{
+    dim3 grid((g.NX + 255) / 256, 18);
+    halo_pack_kernel<<<grid, 256, 0, s>>>(planes, send_lo, send_hi, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_halo_unpack(double* planes, const double* recv_lo, const double* recv_hi, const LbmGeom& g, cudaStream_t s)
+{
+    dim3 grid((g.NX + 255) / 256, 18);
+    halo_unpack_kernel<<<grid, 256, 0, s>>>(planes, recv_lo, recv_hi, g);
     return cudaGetLastError();
 }
 cudaError_t launch_fill(double* p, double v, size_t n, cudaStream_t s)

@@ -14,6 +14,9 @@ cudaError_t launch_soa_to_aos(const double* planes, double* aos, int species, in
 // including halo rows.  NY = global rows, y0 = first global row of the slab.
 cudaError_t launch_initialize(double* planes, const LbmGeom& g, int NY, int y0,
                               const double rho_init[3], const double T_init[3], const double w[3], cudaStream_t s);
+// K5: 18 boundary rows per side (see layout.cu); send_* / recv_* are [18][NX]
+cudaError_t launch_halo_pack(const double* planes, double* send_lo, double* send_hi, const LbmGeom& g, cudaStream_t s);
+cudaError_t launch_halo_unpack(double* planes, const double* recv_lo, const double* recv_hi, const LbmGeom& g, cudaStream_t s);
 cudaError_t launch_fill(double* p, double v, size_t n, cudaStream_t s);
 
 } // namespace plbm

@@ -67,6 +67,11 @@ struct plbm_ctx {
     // spectral Poisson
     PoissonFftDev fft = {};
     cpx* tw_row = nullptr; cpx* tw_col = nullptr; double* sx2 = nullptr; double* sy2 = nullptr;
+    // multi-slab exchange buffers
+    double* halo_send_lo = nullptr; double* halo_send_hi = nullptr; double* halo_recv_lo = nullptr; double* halo_recv_hi = nullptr;
+    double* phi_below = nullptr; double* phi_above = nullptr;
+    int slab_y0[PLBM_MAX_RANKS + 1] = {};
+    int slab_k0[PLBM_MAX_RANKS + 1] = {};
     long long bytes = 0;
     std::vector<cudaEvent_t> events;
 };
@@ -125,10 +130,10 @@ int build_consts(plbm_ctx* c)
 
 int build_fft(plbm_ctx* c)
 {
-    const int NX = c->cfg.NX, NY = c->cfg.NY;
-    if (c->cfg.nranks != 1) return fail("spectral Poisson: multi-rank transpose is driven by the host layer (nranks=%d)", c->cfg.nranks);
+    const int NX = c->cfg.NX, NY = c->cfg.NY, R = c->cfg.nranks;
     if (NX > FFT_MAX_N || NY > FFT_MAX_N) return fail("spectral Poisson supports NX, NY <= %d (got %dx%d)", FFT_MAX_N, NX, NY);
-    const int n0 = NX, n1 = NY, nh = n1 / 2 + 1;
+    if (R > 1 && NX != NY) return fail("spectral Poisson on several slabs needs NX == NY (the reference reshapes the flat array as NX rows of NY, src/poisson.cpp:621)");
+    const int n0 = NX, n1 = NY, nh = n1 / 2 + 1, nyl = (R > 1) ? c->geom.NYl : n0;
     std::vector<double> tw((size_t)2 * (n0 > n1 ? n0 : n1));
     if (dev_alloc(c, &c->tw_row, n1)) return 1;
     host_twiddles(n1, tw.data());
@@ -143,12 +148,22 @@ int build_fft(plbm_ctx* c)
     if (dev_alloc(c, &c->sy2, nh)) return 1;
     host_sin2_cols(NY, s2.data());
     CUDA_TRY(cudaMemcpy(c->sy2, s2.data(), sizeof(double) * nh, cudaMemcpyHostToDevice));
-    if (dev_alloc(c, &c->fft.T, (size_t)nh * n0)) return 1;
-    c->fft.n0 = n0; c->fft.n1 = n1;
-    c->fft.row.n = n1; c->fft.row.nstages = host_factorize(n1, c->fft.row.radix); c->fft.row.tw = c->tw_row;
-    c->fft.col.n = n0; c->fft.col.nstages = host_factorize(n0, c->fft.col.radix); c->fft.col.tw = c->tw_col;
-    c->fft.sx2 = c->sx2; c->fft.sy2 = c->sy2;
-    c->fft.norm = 1.0 / (NX * NY);                         // reference src/poisson.cpp:415
+    PoissonFftDev& f = c->fft;
+    f.n0 = n0; f.n1 = n1; f.nyl = nyl;
+    f.tab.nranks = R;
+    for (int r = 0; r <= R; ++r) {
+        f.tab.y0[r] = (R > 1) ? c->slab_y0[r] : (r == 0 ? 0 : n0);
+        c->slab_k0[r] = (int)(((long long)nh * r) / R);
+    }
+    f.k0 = c->slab_k0[c->cfg.rank];
+    f.tab.nkl = c->slab_k0[c->cfg.rank + 1] - f.k0;
+    if (dev_alloc(c, &f.T1, (size_t)nh * nyl)) return 1;
+    if (R > 1) { if (dev_alloc(c, &f.T2, (size_t)(f.tab.nkl > 0 ? f.tab.nkl : 1) * n0)) return 1; }
+    else f.T2 = f.T1;
+    f.row.n = n1; f.row.nstages = host_factorize(n1, f.row.radix); f.row.tw = c->tw_row;
+    f.col.n = n0; f.col.nstages = host_factorize(n0, f.col.radix); f.col.tw = c->tw_col;
+    f.sx2 = c->sx2; f.sy2 = c->sy2;
+    f.norm = 1.0 / (NX * NY);                              // reference src/poisson.cpp:415
     CUDA_TRY(poisson_fft_configure());
     return 0;
 }
@@ -171,8 +186,11 @@ int poisson_first_call(plbm_ctx* c)
 int poisson_solver(plbm_ctx* c, int type, long long* launches)
 {
     if (type == PLBM_POISSON_FFT) {
-        if (!c->fft.T) return fail("spectral Poisson was not set up for this context (poisson_type must be FFT at creation)");
-        CUDA_TRY(launch_poisson_fft(c->fft, c->rho_q, c->phi, c->stream));
+        if (!c->fft.T1) return fail("spectral Poisson was not set up for this context (poisson_type must be FFT at creation)");
+        if (c->cfg.nranks != 1) return fail("several slabs: drive the Poisson stages with plbm_poisson_stage() around the all-to-all exchanges");
+        CUDA_TRY(launch_poisson_rows_fwd(c->fft, c->rho_q, c->stream));
+        CUDA_TRY(launch_poisson_cols(c->fft, c->stream));
+        CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream));
         if (launches) *launches += 3;
         return 0;
     }
@@ -183,7 +201,9 @@ int poisson_solver(plbm_ctx* c, int type, long long* launches)
 int poisson_efield(plbm_ctx* c, int bc, long long* launches)
 {
     if (bc == PLBM_BC_PERIODIC) {
-        CUDA_TRY(launch_efield_periodic(c->phi, c->Ex, c->Ey, c->cfg.NX, c->cfg.NY, c->stream));
+        const bool slabs = c->cfg.nranks > 1;
+        CUDA_TRY(launch_efield_periodic(c->phi, slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr, c->Ex, c->Ey,
+                                        c->cfg.NX, c->geom.NYl, c->stream));
         if (launches) *launches += 1;
         return 0;
     }
@@ -265,9 +285,16 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     plbm_ctx* c = new plbm_ctx();
     c->cfg = *cfg;
     if (c->cfg.nranks <= 1) { c->cfg.nranks = 1; c->cfg.rank = 0; c->cfg.y0 = 0; c->cfg.NY_local = cfg->NY; }
-    if (c->cfg.y0 < 0 || c->cfg.NY_local < 1 || c->cfg.y0 + c->cfg.NY_local > cfg->NY) {
-        delete c;
-        return fail("plbm_create: slab [%d, %d) outside the lattice", cfg->y0, cfg->y0 + cfg->NY_local);
+    else {
+        // the library owns the decomposition rule (plbm_slab_of); y0 / NY_local of the caller are ignored
+        if (c->cfg.nranks > PLBM_MAX_RANKS || c->cfg.rank < 0 || c->cfg.rank >= c->cfg.nranks) { delete c; return fail("plbm_create: rank %d of %d", cfg->rank, cfg->nranks); }
+        for (int r = 0; r <= c->cfg.nranks; ++r) {
+            int y0r = 0, nylr = 0;
+            if (r < c->cfg.nranks && plbm_slab_of(cfg->NY, r, c->cfg.nranks, &y0r, &nylr)) { delete c; return 1; }
+            c->slab_y0[r] = (r < c->cfg.nranks) ? y0r : cfg->NY;
+        }
+        c->cfg.y0 = c->slab_y0[c->cfg.rank];
+        c->cfg.NY_local = c->slab_y0[c->cfg.rank + 1] - c->cfg.y0;
     }
     c->geom.NX = cfg->NX;
     c->geom.NYl = c->cfg.NY_local;
@@ -295,6 +322,14 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     CUDA_OR_DESTROY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
     CUDA_OR_DESTROY(launch_fill(c->Ex, cfg->Ex_ext, n, c->stream));        // reference src/plasma.cpp:116-117
     CUDA_OR_DESTROY(launch_fill(c->Ey, cfg->Ey_ext, n, c->stream));
+    if (c->cfg.nranks > 1) {
+        const size_t hn = (size_t)18 * cfg->NX;
+        TRY_OR_DESTROY(dev_alloc(c, &c->halo_send_lo, hn)); TRY_OR_DESTROY(dev_alloc(c, &c->halo_send_hi, hn));
+        TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_lo, hn)); TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_hi, hn));
+        TRY_OR_DESTROY(dev_alloc(c, &c->phi_below, (size_t)cfg->NX)); TRY_OR_DESTROY(dev_alloc(c, &c->phi_above, (size_t)cfg->NX));
+        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_below, 0, sizeof(double) * cfg->NX, c->stream));
+        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_above, 0, sizeof(double) * cfg->NX, c->stream));
+    }
     TRY_OR_DESTROY(build_consts(c));
     if (cfg->poisson_type == PLBM_POISSON_FFT && cfg->bc_type == PLBM_BC_PERIODIC) TRY_OR_DESTROY(build_fft(c));
     CUDA_OR_DESTROY(cudaStreamSynchronize(c->stream));
@@ -313,7 +348,11 @@ void plbm_destroy(plbm_ctx* c)
     cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
     for (int k = 0; k < 12; ++k) cudaFree(c->macro[k]);
     cudaFree(c->staging);
-    cudaFree(c->tw_row); cudaFree(c->tw_col); cudaFree(c->sx2); cudaFree(c->sy2); cudaFree(c->fft.T);
+    cudaFree(c->tw_row); cudaFree(c->tw_col); cudaFree(c->sx2); cudaFree(c->sy2);
+    if (c->fft.T2 != c->fft.T1) cudaFree(c->fft.T2);
+    cudaFree(c->fft.T1);
+    cudaFree(c->halo_send_lo); cudaFree(c->halo_send_hi); cudaFree(c->halo_recv_lo); cudaFree(c->halo_recv_hi);
+    cudaFree(c->phi_below); cudaFree(c->phi_above);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -371,6 +410,7 @@ int plbm_set_efield(plbm_ctx* c, const double* Ex, const double* Ey)
 int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
 {
     if (!c) return fail("plbm_step: null context");
+    if (c->cfg.nranks > 1) return fail("plbm_step: this context is one slab of %d; drive it with plbm_step_local / plbm_halo_* / plbm_poisson_stage", c->cfg.nranks);
     for (int t = 0; t < nsteps; ++t) {
         if (one_step(c, want_fields && t == nsteps - 1, nullptr)) return 1;
         if (solve_poisson(c, nullptr)) return 1;
@@ -409,6 +449,7 @@ int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, f
 {
     if (!c) return fail("plbm_step_timed: null context");
     if (nsteps < 1 || nsteps > 100000) return fail("plbm_step_timed: nsteps out of range");
+    if (c->cfg.nranks > 1) return fail("plbm_step_timed: single-slab contexts only");
     const size_t need = (size_t)2 * nsteps + 1;
     while (c->events.size() < need) {
         cudaEvent_t e;
@@ -476,6 +517,73 @@ int plbm_host_efield(plbm_ctx* c, int bc_type, double* Ex, double* Ey)
     CUDA_TRY(cudaMemcpyAsync(Ex, c->Ex, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(Ey, c->Ey, bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_slab_of(int NY, int rank, int nranks, int* y0, int* ny_local)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("plbm_slab_of: rank %d of %d", rank, nranks);
+    if (nranks == 1) { if (y0) *y0 = 0; if (ny_local) *ny_local = NY; return 0; }
+    if (NY % 2) return fail("plbm_slab_of: NY must be even to cut slabs (the spectral solve transforms rows in pairs)");
+    const long long pairs = NY / 2;
+    const int a = (int)(2 * ((pairs * rank) / nranks)), b = (int)(2 * ((pairs * (rank + 1)) / nranks));
+    if (b - a < 2) return fail("plbm_slab_of: %d rows cannot feed %d slabs", NY, nranks);
+    if (y0) *y0 = a;
+    if (ny_local) *ny_local = b - a;
+    return 0;
+}
+
+int plbm_step_local(plbm_ctx* c, int want_fields)
+{
+    if (!c) return fail("plbm_step_local: null context");
+    return one_step(c, want_fields != 0, nullptr);
+}
+
+int plbm_halo_pack(plbm_ctx* c)
+{
+    if (!c || c->cfg.nranks < 2) return fail("plbm_halo_pack: needs a multi-slab context");
+    CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->halo_send_lo, c->halo_send_hi, c->geom, c->stream));
+    return 0;
+}
+
+int plbm_halo_unpack(plbm_ctx* c)
+{
+    if (!c || c->cfg.nranks < 2) return fail("plbm_halo_unpack: needs a multi-slab context");
+    CUDA_TRY(launch_halo_unpack(c->pop[c->cur], c->halo_recv_lo, c->halo_recv_hi, c->geom, c->stream));
+    return 0;
+}
+
+int plbm_poisson_stage(plbm_ctx* c, int stage)
+{
+    if (!c) return fail("plbm_poisson_stage: null context");
+    if (poisson_first_call(c)) return 1;
+    const int type = c->cfg.poisson_type;
+    if (type == PLBM_POISSON_NONE) return 0;
+    if (type != PLBM_POISSON_FFT || c->cfg.bc_type != PLBM_BC_PERIODIC) return fail("plbm_poisson_stage: only the periodic spectral solve runs on several slabs");
+    switch (stage) {
+    case 0: CUDA_TRY(launch_poisson_rows_fwd(c->fft, c->rho_q, c->stream)); return 0;
+    case 1: CUDA_TRY(launch_poisson_cols(c->fft, c->stream)); return 0;
+    case 2: CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream)); return 0;
+    case 3: return poisson_efield(c, PLBM_BC_PERIODIC, nullptr);
+    default: return fail("plbm_poisson_stage: stage %d", stage);
+    }
+}
+
+int plbm_exchange_info(plbm_ctx* c, plbm_exchange* o)
+{
+    if (!c || !o) return fail("plbm_exchange_info: null argument");
+    std::memset(o, 0, sizeof(*o));
+    const int R = c->cfg.nranks, nh = c->cfg.NY / 2 + 1;
+    o->nranks = R; o->rank = c->cfg.rank;
+    o->halo_send_lo = c->halo_send_lo; o->halo_send_hi = c->halo_send_hi;
+    o->halo_recv_lo = c->halo_recv_lo; o->halo_recv_hi = c->halo_recv_hi;
+    o->halo_count = (long long)18 * c->cfg.NX;
+    o->phi_first_row = c->phi; o->phi_last_row = c->phi + (size_t)(c->geom.NYl - 1) * c->cfg.NX;
+    o->phi_below = c->phi_below; o->phi_above = c->phi_above;
+    o->phi_count = c->cfg.NX;
+    o->t1 = c->fft.T1; o->t2 = c->fft.T2;
+    for (int r = 0; r <= R; ++r) { o->slab_y0[r] = (R > 1) ? c->slab_y0[r] : (r ? c->cfg.NY : 0); o->slab_k0[r] = c->fft.T1 ? c->slab_k0[r] : 0; }
+    (void)nh;
     return 0;
 }
 

@@ -21,12 +21,14 @@
 
 namespace plbm {
 
+// `in` holds the nyl local rows; T1 is [nh][nyl] (local rows), so the block of spectral columns a
+// peer owns is contiguous and can be sent as is.
 __global__ void __launch_bounds__(1024)
 poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
                         int n0, int n1, int nh)
 {
     extern __shared__ cpx fbuf[];
-    const int ra = 2 * blockIdx.x, rb = ra + 1;
+    const int ra = 2 * blockIdx.x, rb = ra + 1;        // local row pair; n0 = number of LOCAL rows here
     const bool paired = rb < n0;
     const double* rowa = in + (size_t)ra * n1;
     const double* rowb = in + (size_t)rb * n1;
@@ -54,17 +56,22 @@ poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, cons
     }
 }
 
-// One spectral column k (all kx): forward, phi_hat = rho_hat / denom (poisson.cpp:388-409), inverse.
+// One spectral column (all kx): forward, phi_hat = rho_hat / denom (poisson.cpp:388-409), inverse.
+// T2 holds this rank's columns as received from every rank s: [s][k_local][rows of s].
 __global__ void __launch_bounds__(1024)
 poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
-                    const double* __restrict__ sx2, const double* __restrict__ sy2, int n0)
+                    const double* __restrict__ sx2, const double* __restrict__ sy2, int n0,
+                    const __grid_constant__ SlabTable tab, int k0)
 {
     extern __shared__ cpx fbuf[];
-    const int k = blockIdx.x;
-    cpx* col = T + (size_t)k * n0;
-    for (int r = threadIdx.x; r < n0; r += blockDim.x) fbuf[r] = col[r];
+    const int kl = blockIdx.x;
+    for (int sr = 0; sr < tab.nranks; ++sr) {
+        const int rows = tab.y0[sr + 1] - tab.y0[sr];
+        const cpx* seg = T + (size_t)tab.nkl * tab.y0[sr] + (size_t)kl * rows;
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) fbuf[tab.y0[sr] + r] = seg[r];
+    }
     fft_smem<-1>(fbuf, plan);
-    const double syk = __ldg(sy2 + k);
+    const double syk = __ldg(sy2 + k0 + kl);
     for (int i = threadIdx.x; i < n0; i += blockDim.x) {
         const double denom = __dmul_rn(4.0, __dadd_rn(__ldg(sx2 + i), syk));
         cpx v = fbuf[i];
@@ -77,7 +84,11 @@ poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
         fbuf[i] = v;
     }
     fft_smem<+1>(fbuf, plan);
-    for (int r = threadIdx.x; r < n0; r += blockDim.x) col[r] = fbuf[r];
+    for (int sr = 0; sr < tab.nranks; ++sr) {
+        const int rows = tab.y0[sr + 1] - tab.y0[sr];
+        cpx* seg = T + (size_t)tab.nkl * tab.y0[sr] + (size_t)kl * rows;
+        for (int r = threadIdx.x; r < rows; r += blockDim.x) seg[r] = fbuf[tab.y0[sr] + r];
+    }
 }
 
 __global__ void __launch_bounds__(1024)
@@ -107,18 +118,20 @@ poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, con
     }
 }
 
-// K3, poisson.cpp:589-607
-__global__ void efield_periodic_kernel(const double* __restrict__ phi, double* __restrict__ Ex, double* __restrict__ Ey,
-                                       int NX, int NY)
+// K3, poisson.cpp:589-607.  NY = local rows; below/above = the neighbouring slabs' boundary rows of
+// phi (nullptr: single slab, wrap inside the array).
+__global__ void efield_periodic_kernel(const double* __restrict__ phi, const double* __restrict__ below, const double* __restrict__ above,
+                                       double* __restrict__ Ex, double* __restrict__ Ey, int NX, int NY)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (i >= NX) return;
     const int im1 = (i == 0) ? NX - 1 : i - 1, ip1 = (i == NX - 1) ? 0 : i + 1;
-    const int jm1 = (j == 0) ? NY - 1 : j - 1, jp1 = (j == NY - 1) ? 0 : j + 1;
     const size_t row = (size_t)j * NX;
+    const double* rm = (j > 0) ? phi + row - NX : (below ? below : phi + (size_t)(NY - 1) * NX);
+    const double* rp = (j < NY - 1) ? phi + row + NX : (above ? above : phi);
     Ex[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(phi + row + ip1), __ldg(phi + row + im1)));
-    Ey[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(phi + (size_t)jp1 * NX + i), __ldg(phi + (size_t)jm1 * NX + i)));
+    Ey[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(rp + i), __ldg(rm + i)));
 }
 
 static int fft_threads(int n)
@@ -140,20 +153,30 @@ cudaError_t poisson_fft_configure()
     return cudaSuccess;
 }
 
-cudaError_t launch_poisson_fft(const PoissonFftDev& p, const double* rho_q, double* phi, cudaStream_t stream)
+cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream)
 {
-    const int n0 = p.n0, n1 = p.n1, nh = n1 / 2 + 1;
-    const int npairs = (n0 + 1) / 2;
-    poisson_rows_fwd_kernel<<<npairs, fft_threads(n1), sizeof(cpx) * n1, stream>>>(rho_q, p.T, p.row, n0, n1, nh);
-    poisson_cols_kernel<<<nh, fft_threads(n0), sizeof(cpx) * n0, stream>>>(p.T, p.col, p.sx2, p.sy2, n0);
-    poisson_rows_inv_kernel<<<npairs, fft_threads(n1), sizeof(cpx) * n1, stream>>>(p.T, phi, p.row, n0, n1, nh, p.norm);
+    const int nh = p.n1 / 2 + 1;
+    poisson_rows_fwd_kernel<<<(p.nyl + 1) / 2, fft_threads(p.n1), sizeof(cpx) * p.n1, stream>>>(rho_q, p.T1, p.row, p.nyl, p.n1, nh);
+    return cudaGetLastError();
+}
+cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream)
+{
+    if (p.tab.nkl > 0)
+        poisson_cols_kernel<<<p.tab.nkl, fft_threads(p.n0), sizeof(cpx) * p.n0, stream>>>(p.T2, p.col, p.sx2, p.sy2, p.n0, p.tab, p.k0);
+    return cudaGetLastError();
+}
+cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream)
+{
+    const int nh = p.n1 / 2 + 1;
+    poisson_rows_inv_kernel<<<(p.nyl + 1) / 2, fft_threads(p.n1), sizeof(cpx) * p.n1, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
     return cudaGetLastError();
 }
 
-cudaError_t launch_efield_periodic(const double* phi, double* Ex, double* Ey, int NX, int NY, cudaStream_t stream)
+cudaError_t launch_efield_periodic(const double* phi, const double* below, const double* above, double* Ex, double* Ey,
+                                   int NX, int NYl, cudaStream_t stream)
 {
-    dim3 grid((NX + 255) / 256, NY);
-    efield_periodic_kernel<<<grid, 256, 0, stream>>>(phi, Ex, Ey, NX, NY);
+    dim3 grid((NX + 255) / 256, NYl);
+    efield_periodic_kernel<<<grid, 256, 0, stream>>>(phi, below, above, Ex, Ey, NX, NYl);
     return cudaGetLastError();
 }
 

@@ -5,17 +5,33 @@
 
 namespace plbm {
 
+constexpr int PLBM_MAX_RANKS = 16;
+
+// Row ranges of all slabs and this rank's share of the spectral columns.
+struct SlabTable {
+    int nranks;
+    int y0[PLBM_MAX_RANKS + 1];   // rank s owns FFT rows [y0[s], y0[s+1])
+    int nkl;                      // spectral columns owned by this rank
+};
+
 struct PoissonFftDev {
     int n0, n1;          // n0 = NX "rows" of n1 = NY contiguous values (poisson.cpp:621-622)
+    int nyl;             // local rows (n0 for a single slab)
+    int k0;              // first spectral column owned by this rank
+    SlabTable tab;
     FftPlan row, col;    // length n1 / length n0
-    cpx* T;              // (n1/2+1) x n0 transposed half spectrum
+    cpx* T1;             // [n1/2+1][nyl]  half spectrum of the local rows, column-major
+    cpx* T2;             // [rank s][nkl][rows of s]  this rank's columns after the exchange (== T1 for one slab)
     const double* sx2;   // sin^2(pi*kx/NX) per row index i        (poisson.cpp:391-395)
     const double* sy2;   // sin^2(pi*ky/NY) per column index j
     double norm;         // 1.0 / (NX*NY)                           (poisson.cpp:415)
 };
 
 cudaError_t poisson_fft_configure();
-cudaError_t launch_poisson_fft(const PoissonFftDev& p, const double* rho_q, double* phi, cudaStream_t stream);
-cudaError_t launch_efield_periodic(const double* phi, double* Ex, double* Ey, int NX, int NY, cudaStream_t stream);
+cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream);   // rho_q -> T1
+cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream);                            // T2 in place
+cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream);           // T1 -> phi
+cudaError_t launch_efield_periodic(const double* phi, const double* below, const double* above, double* Ex, double* Ey,
+                                   int NX, int NYl, cudaStream_t stream);
 
 } // namespace plbm

@@ -1,0 +1,185 @@
+"""Host layer for several GPUs of one node: one process per GPU, the lattice cut into y-slabs.
+
+The data path has exactly two exchanges per time step:
+  * halo: the 18 population rows (3 outgoing directions x 6 distributions) that leave the slab on
+    each side travel to the periodic neighbours                       -- point-to-point send/recv
+  * Poisson: the half spectrum of the local rows is transposed to "all rows of my spectral
+    columns" and back                                                  -- two all-to-alls
+plus one row of the potential per side for E = -grad(phi).  `SlabDriver` sequences these around the
+library's per-slab kernels (plbm_step_local, plbm_halo_pack/unpack, plbm_poisson_stage) through
+torch.distributed (NCCL on GPUs).  The kernels come from a backend object so that the sequencing,
+the neighbour map and the split sizes can be exercised on CPU with the gloo backend and a test
+double (tests/slab_double.py); the product backend is `CudaSlabBackend` below, a thin ctypes binding
+with no arithmetic of its own.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .api import PlasmaLBM, PlbmError, _check
+
+
+class PlbmExchange(C.Structure):
+    _fields_ = [("nranks", C.c_int), ("rank", C.c_int),
+                ("halo_send_lo", C.c_void_p), ("halo_send_hi", C.c_void_p), ("halo_recv_lo", C.c_void_p), ("halo_recv_hi", C.c_void_p),
+                ("halo_count", C.c_longlong),
+                ("phi_first_row", C.c_void_p), ("phi_last_row", C.c_void_p), ("phi_below", C.c_void_p), ("phi_above", C.c_void_p),
+                ("phi_count", C.c_longlong),
+                ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("slab_y0", C.c_int * 17), ("slab_k0", C.c_int * 17)]
+
+
+def slab_of(NY: int, rank: int, nranks: int):
+    """The library's decomposition rule (plbm_slab_of): balanced, even-sized slabs."""
+    from .api import load_library
+    lib = load_library()
+    lib.plbm_slab_of.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    y0, nyl = C.c_int(), C.c_int()
+    _check(lib, lib.plbm_slab_of(NY, rank, nranks, C.byref(y0), C.byref(nyl)), "plbm_slab_of")
+    return y0.value, nyl.value
+
+
+class _DeviceMemory:
+    """A raw device allocation exposed through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class CudaSlabBackend:
+    """One slab on one GPU: the library context plus torch views of its exchange buffers."""
+
+    def __init__(self, NX: int, NY: int, rank: int, nranks: int, poisson: str = "fft", device: int = 0, **si):
+        import torch
+        self.torch = torch
+        self.sim = PlasmaLBM(NX, NY, poisson=poisson, rank=rank, nranks=nranks, device=device, **si)
+        lib = self.sim.lib
+        for name in ("plbm_step_local", "plbm_poisson_stage"):
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_int]
+        for name in ("plbm_halo_pack", "plbm_halo_unpack"):
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.plbm_exchange_info.argtypes = [C.c_void_p, C.POINTER(PlbmExchange)]
+        self.lib = lib
+        x = PlbmExchange()
+        _check(lib, lib.plbm_exchange_info(self.sim._h, C.byref(x)), "plbm_exchange_info")
+        self.rank, self.nranks = rank, nranks
+        self.slab_y0 = list(x.slab_y0[: nranks + 1])
+        self.slab_k0 = list(x.slab_k0[: nranks + 1])
+        self.NX, self.NY = NX, NY
+        self.has_poisson = poisson == "fft"
+        dev = torch.device("cuda", device)
+        view = lambda ptr, n: torch.as_tensor(_DeviceMemory(ptr, n), device=dev)
+        self.halo_send_lo = view(x.halo_send_lo, x.halo_count); self.halo_send_hi = view(x.halo_send_hi, x.halo_count)
+        self.halo_recv_lo = view(x.halo_recv_lo, x.halo_count); self.halo_recv_hi = view(x.halo_recv_hi, x.halo_count)
+        self.phi_first_row = view(x.phi_first_row, x.phi_count); self.phi_last_row = view(x.phi_last_row, x.phi_count)
+        self.phi_below = view(x.phi_below, x.phi_count); self.phi_above = view(x.phi_above, x.phi_count)
+        if self.has_poisson:
+            nh, nyl = NY // 2 + 1, self.slab_y0[rank + 1] - self.slab_y0[rank]
+            nkl = self.slab_k0[rank + 1] - self.slab_k0[rank]
+            self.t1 = view(x.t1, 2 * nh * nyl)
+            self.t2 = view(x.t2, 2 * max(nkl, 1) * NX)[: 2 * nkl * NX]
+        # NCCL work is ordered against the library's own stream
+        self.stream = torch.cuda.ExternalStream(self.sim.stream, device=dev)
+
+    def step_local(self, want_fields: bool):
+        _check(self.lib, self.lib.plbm_step_local(self.sim._h, int(want_fields)), "plbm_step_local")
+
+    def halo_pack(self):
+        _check(self.lib, self.lib.plbm_halo_pack(self.sim._h), "plbm_halo_pack")
+
+    def halo_unpack(self):
+        _check(self.lib, self.lib.plbm_halo_unpack(self.sim._h), "plbm_halo_unpack")
+
+    def poisson_stage(self, stage: int):
+        _check(self.lib, self.lib.plbm_poisson_stage(self.sim._h, stage), "plbm_poisson_stage")
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self.stream)
+
+    def fields(self, names=None):
+        return self.sim.fields(names) if names else self.sim.fields()
+
+    def sync(self):
+        self.sim.sync()
+
+    def close(self):
+        self.sim.close()
+
+
+class SlabDriver:
+    """Sequences one time step over all slabs.  `backend` provides the per-slab kernels and the
+    exchange buffers (torch tensors on the backend's device); `dist` is torch.distributed."""
+
+    def __init__(self, backend, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.b = backend
+        self.group = group
+        self.rank, self.nranks = backend.rank, backend.nranks
+        if self.nranks < 2:
+            raise PlbmError("SlabDriver needs at least two slabs; use PlasmaLBM for one GPU")
+        self.up = (self.rank + 1) % self.nranks       # owns the rows above mine (periodic)
+        self.down = (self.rank - 1) % self.nranks
+        y0, k0 = backend.slab_y0, backend.slab_k0
+        nyl = y0[self.rank + 1] - y0[self.rank]
+        nkl = k0[self.rank + 1] - k0[self.rank]
+        # all-to-all split sizes in doubles (complex = 2): T1 -> T2 and back
+        self.t1_splits = [2 * (k0[d + 1] - k0[d]) * nyl for d in range(self.nranks)]
+        self.t2_splits = [2 * nkl * (y0[s + 1] - y0[s]) for s in range(self.nranks)]
+
+    def _sendrecv(self, send_up, send_down, recv_from_down, recv_from_up):
+        """What I send up is what my upper neighbour receives from below, and vice versa.  With two
+        slabs both neighbours are the same rank: the order send(up), send(down) / recv(down), recv(up)
+        pairs the messages correctly because point-to-point traffic between two ranks is ordered."""
+        d = self.dist
+        ops = [d.P2POp(d.isend, send_up, self.up, self.group), d.P2POp(d.isend, send_down, self.down, self.group),
+               d.P2POp(d.irecv, recv_from_down, self.down, self.group), d.P2POp(d.irecv, recv_from_up, self.up, self.group)]
+        for w in d.batch_isend_irecv(ops):
+            w.wait()
+
+    def step(self, nsteps: int = 1, want_fields: bool = False, timing=None):
+        """nsteps time steps.  timing: optional list that receives one (start, end) CUDA event pair
+        around every fused collide-stream launch (CUDA backend only)."""
+        b, d = self.b, self.dist
+        with b.stream_context():
+            for t in range(nsteps):
+                if timing is not None:
+                    e0, e1 = b.torch.cuda.Event(enable_timing=True), b.torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                b.step_local(want_fields and t == nsteps - 1)
+                if timing is not None:
+                    e1.record()
+                    timing.append((e0, e1))
+                # halo: top row's upward populations go up, bottom row's downward populations go down
+                b.halo_pack()
+                self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi)
+                b.halo_unpack()
+                # spectral Poisson with two transposes
+                b.poisson_stage(0)
+                if b.has_poisson:
+                    d.all_to_all_single(b.t2, b.t1, self.t2_splits, self.t1_splits, group=self.group)
+                    b.poisson_stage(1)
+                    d.all_to_all_single(b.t1, b.t2, self.t1_splits, self.t2_splits, group=self.group)
+                    b.poisson_stage(2)
+                    # my top phi row is the row below my upper neighbour's slab, my bottom row the one above my lower neighbour's
+                    self._sendrecv(b.phi_last_row, b.phi_first_row, b.phi_below, b.phi_above)
+                    b.poisson_stage(3)
+
+    def gather_fields(self, names):
+        """All slabs' fields on every rank as full [NY, NX] arrays (tests, output)."""
+        import torch
+        mine = self.b.fields(names)
+        rows = [self.b.slab_y0[s + 1] - self.b.slab_y0[s] for s in range(self.nranks)]
+        pad = max(rows)
+        nccl = self.dist.get_backend(self.group) == "nccl"
+        dev = self.b.halo_send_lo.device if nccl else torch.device("cpu")
+        out = {}
+        for n in names:
+            t = torch.zeros((pad, self.b.NX), dtype=torch.float64)
+            t[: rows[self.rank]] = torch.from_numpy(np.ascontiguousarray(mine[n]))
+            parts = [torch.empty((pad, self.b.NX), dtype=torch.float64, device=dev) for _ in range(self.nranks)]
+            self.dist.all_gather(parts, t.to(dev), group=self.group)
+            out[n] = torch.cat([p[: rows[s]].cpu() for s, p in enumerate(parts)], 0).numpy()
+        return out

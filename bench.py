@@ -175,11 +175,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU slab decomposition is not wired up yet in this revision")
-
-    nx = args.nx or 2048
     K, W = args.steps, max(args.warmup, 3)
+    peak, peak_src = hbm_peak()
+    if world > 1:
+        multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src)
+        return
+    nx = args.nx or 2048
     sim = P.PlasmaLBM(nx, nx, poisson=args.poisson, device=local_rank)
     sim.step(W)
     sim.sync()
@@ -191,32 +192,11 @@ def main():
     cells = nx * nx
     mlups = cells * K / (ms_total * 1e-3) / 1e6
     k1_ms = t["ms_k1"] / K
-    peak, peak_src = hbm_peak()
     achieved = K1_BYTES_PER_UPDATE * cells / (k1_ms * 1e-3) / 1e9
-    traffic = None
-    tfile = ROOT / "profiles" / "k1_traffic.json"       # dram bytes per launch from the committed ncu capture
-    if tfile.exists():
-        try:
-            rec = json.loads(tfile.read_text())
-            if rec.get("nx") == nx:
-                traffic = rec.get("dram_bytes_per_launch")
-        except Exception:
-            pass
-
-    line = {"metric": "MLUPS (all species)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{nx}x{nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic "
-                                   f"(BASELINE.json configs[2])",
-                       "initial_condition": "reference Initialize(): e/i block in the central square, neutrals uniform",
-                       "l2": f"state 2 x {54 * 8 * cells / 1e9:.2f} GB streams through HBM every step (inputs larger than L2, no flush needed)",
-                       "bytes_per_update_k1": K1_BYTES_PER_UPDATE, "bytes_per_update_step": STEP_BYTES_PER_UPDATE,
-                       "hbm_gbs_whole_step": STEP_BYTES_PER_UPDATE * mlups * 1e-3},
-            "roofline": {"bound": "hbm", "kernel": "k1_fused_kernel<false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "k1_ms_per_launch": k1_ms, "k1_share_of_step": t["ms_k1"] / ms_total},
-            "clocks": clocks.summary(),
-            "gpu_launches": t["launches"]}
+    line = base_line(args, nx, world, K, W, ms_total, mlups, "configs[2]")
+    line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, k1_ms, t["ms_k1"] / ms_total)
+    line["clocks"] = clocks.summary()
+    line["gpu_launches"] = t["launches"]
 
     # ---- e2e: public API with host buffers -------------------------------------------------
     if not args.no_e2e:
@@ -243,12 +223,8 @@ def main():
                 raise SystemExit(lib.plbm_last_error().decode())
         sim.sync()
         dt = time.perf_counter() - t0
-        h2d = 6 * 9 * cells * 8 / Ke
-        d2h = len(P.FIELD_NAMES) * cells * 8
-        line["e2e"] = {"value": cells * Ke / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "steps": Ke, "what": "plbm_upload_state of the 6 AoS population arrays from pinned host memory (once, amortised "
-                                            "over the steps), then per step plbm_step + plbm_download_fields of the 15 visualised fields "
-                                            "+ phi into pinned host memory, as LBmethod::Run_simulation hands them to the visualiser"}
+        line["e2e"] = {"value": cells * Ke / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 6 * 9 * cells * 8 / Ke,
+                       "d2h_bytes_per_step": len(P.FIELD_NAMES) * cells * 8, "steps": Ke, "what": E2E_WHAT}
         del f_host, g_host, out_host
 
     # ---- cpu baseline (bounded sample of the same workload) -------------------------------
@@ -258,12 +234,106 @@ def main():
             v, kind, info = run_cpu_reference(nx, args.cpu_steps, args.poisson, threads)
             line["cpu_baseline"] = {"value": v, "unit": "MLUPS", "cores": threads, "kind": kind,
                                     "sample": f"{nx}x{nx}, {args.cpu_steps} time steps (time loop only), unmodified reference sources, "
-                                              f"FFTW replaced by oracle/fft_oracle.c, visualisation disabled",
-                                    "phase_s": info.get("phase_s")}
+                                              f"FFTW replaced by oracle/fft_oracle.c, visualisation disabled"}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": threads, "kind": "unavailable", "sample": str(e)[:200]}
     sim.close()
     print(json.dumps(line), flush=True)
+
+
+E2E_WHAT = ("plbm_upload_state of the 6 AoS population arrays from pinned host memory (once, amortised over the steps), then per "
+            "step the time step + plbm_download_fields of the 15 visualised fields + phi into pinned host memory, as "
+            "LBmethod::Run_simulation hands them to the visualiser")
+
+# weak scaling: constant cells per GPU (2048^2) on square lattices of side ~ sqrt(N), like the reference's own weak-scaling
+# runs (build/weak_scalability.py); sides chosen with small prime factors for the spectral solve
+WEAK_SIDES = {1: 2048, 2: 2880, 4: 4096, 8: 5760}
+
+
+def base_line(args, nx, world, K, W, ms_total, mlups, cfg_name):
+    cells = nx * nx
+    return {"metric": "MLUPS (all species)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{nx}x{nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic "
+                                   f"(BASELINE.json {cfg_name})",
+                       "initial_condition": "reference Initialize(): e/i block in the central square, neutrals uniform",
+                       "l2": f"state 2 x {54 * 8 * cells / world / 1e9:.2f} GB per GPU streams through HBM every step (inputs larger than L2, no flush needed)",
+                       "bytes_per_update_k1": K1_BYTES_PER_UPDATE, "bytes_per_update_step": STEP_BYTES_PER_UPDATE,
+                       "hbm_gbs_whole_step": STEP_BYTES_PER_UPDATE * mlups * 1e-3}}
+
+
+def roofline(nx, cells, achieved, peak, peak_src, k1_ms, share):
+    traffic = None
+    tfile = ROOT / "profiles" / "k1_traffic.json"       # dram bytes per launch from the committed ncu capture
+    if tfile.exists():
+        try:
+            rec = json.loads(tfile.read_text())
+            if rec.get("nx") == nx:
+                traffic = rec.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return {"bound": "hbm", "kernel": "k1_fused_kernel<false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": share}
+
+
+def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
+    """Slab decomposition over `world` GPUs: halo send/recv + two all-to-alls per step (NCCL)."""
+    import torch.distributed as dist
+    nx = args.nx or WEAK_SIDES.get(world) or (int(2048 * world ** 0.5) // 64 * 64)
+    b = P.CudaSlabBackend(nx, nx, rank, world, poisson=args.poisson, device=local_rank)
+    drv = P.SlabDriver(b)
+    drv.step(W)
+    b.sync(); torch.cuda.synchronize(); dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_events = []
+    with ClockSampler(local_rank) as clocks:
+        with b.stream_context():
+            ev0.record()
+        drv.step(K, timing=k1_events)
+        with b.stream_context():
+            ev1.record()
+        b.sync(); torch.cuda.synchronize()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    k1 = torch.tensor([sum(a.elapsed_time(c) for a, c in k1_events) / max(len(k1_events), 1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(k1, op=dist.ReduceOp.MAX)
+    ms_total, k1_ms = float(ms.item()), float(k1.item())
+    cells = nx * nx
+    local_cells = nx * (b.slab_y0[rank + 1] - b.slab_y0[rank])
+    mlups = cells * K / (ms_total * 1e-3) / 1e6
+    line = base_line(args, nx, world, K, W, ms_total, mlups, "configs[4]-style weak scaling, 2048^2 cells per GPU")
+    achieved = K1_BYTES_PER_UPDATE * local_cells / (k1_ms * 1e-3) / 1e9
+    line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, k1_ms, k1_ms * K / ms_total)
+    line["roofline"]["note"] = "per GPU (slowest rank)"
+    line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + 2 all-to-all transposes of the half spectrum + 1 phi row per side"
+    line["clocks"] = clocks.summary()
+    line["gpu_launches"] = K * 8
+    if not args.no_e2e:
+        import ctypes as C
+        Ke = max(1, min(args.e2e_steps, K))
+        nyl = b.slab_y0[rank + 1] - b.slab_y0[rank]
+        out_host = torch.empty((len(P.FIELD_NAMES), nyl, nx), dtype=torch.float64).pin_memory()
+        dp = C.POINTER(C.c_double)
+        outs = (dp * len(P.FIELD_NAMES))(*[C.cast(out_host[k].data_ptr(), dp) for k in range(len(P.FIELD_NAMES))])
+        b.sync(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            drv.step(1, want_fields=True)
+            if b.lib.plbm_download_fields(b.sim._h, outs) != 0:
+                raise SystemExit(b.lib.plbm_last_error().decode())
+        b.sync(); dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": cells * Ke / float(dt.item()) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": len(P.FIELD_NAMES) * cells * 8, "steps": Ke,
+                       "what": "initial state built on the device (plbm_initialize); per step the time step + download of every slab's 15 "
+                               "visualised fields + phi into pinned host memory (all ranks in parallel)"}
+    b.close()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

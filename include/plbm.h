@@ -135,6 +135,33 @@ int plbm_host_solve_poisson(plbm_ctx* ctx, const double* rho_q, double* Ex, doub
 int plbm_host_poisson_solver(plbm_ctx* ctx, int poisson_type, const double* rho_q);
 int plbm_host_efield(plbm_ctx* ctx, int bc_type, double* Ex, double* Ey);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several slabs (one process per GPU).  The lattice is cut along y; the library owns the rule
+ * (plbm_slab_of: even-sized, balanced slabs).  The data path has two exchanges per step, which the
+ * host layer performs between these calls (NCCL send/recv and all-to-all in this repo's driver):
+ *   plbm_step_local                      K1 on the slab (halo rows must be current)
+ *   plbm_halo_pack -> exchange -> plbm_halo_unpack      18 rows of NX doubles per side
+ *   plbm_poisson_stage(0) -> all-to-all T1->T2 -> stage(1) -> all-to-all T2->T1 -> stage(2)
+ *   exchange one row of phi per side -> plbm_poisson_stage(3)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct plbm_exchange {
+    int nranks, rank;
+    void *halo_send_lo, *halo_send_hi, *halo_recv_lo, *halo_recv_hi;   /* device, halo_count doubles each */
+    long long halo_count;
+    void *phi_first_row, *phi_last_row, *phi_below, *phi_above;         /* device, phi_count doubles each */
+    long long phi_count;
+    void *t1, *t2;        /* device, complex<double>: T1 = [NY/2+1][rows of this slab], T2 = [rank s][columns of this rank][rows of s] */
+    int slab_y0[17];      /* slab s owns rows [slab_y0[s], slab_y0[s+1]) */
+    int slab_k0[17];      /* rank d owns spectral columns [slab_k0[d], slab_k0[d+1]) */
+} plbm_exchange;
+
+int plbm_slab_of(int NY, int rank, int nranks, int* y0, int* ny_local);
+int plbm_step_local(plbm_ctx* ctx, int want_fields);
+int plbm_halo_pack(plbm_ctx* ctx);
+int plbm_halo_unpack(plbm_ctx* ctx);
+int plbm_poisson_stage(plbm_ctx* ctx, int stage);
+int plbm_exchange_info(plbm_ctx* ctx, plbm_exchange* out);
+
 /* Introspection used by the benchmarks and tests. */
 int plbm_local_rows(const plbm_ctx* ctx, int* y0, int* ny_local);
 long long plbm_device_bytes(const plbm_ctx* ctx);

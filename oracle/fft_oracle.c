@@ -169,18 +169,21 @@ void offt_plan2d_destroy(offt_plan2d* p)
     free(p);
 }
 
-void offt_r2c_2d(const offt_plan2d* P, const double* in, offt_cpx* out)
+/* Row pass of the r2c transform on `nrows` consecutive rows (pairs (0,1),(2,3),... of the given
+ * block): out[r][k], k = 0..n1/2.  Exposed separately so that the slab-decomposed solve can be
+ * restated on the CPU (tests/slab_double.py). */
+void offt_rows_fwd(const offt_plan2d* P, const double* in, int nrows, offt_cpx* out)
 {
-    const int n0 = P->n0, n1 = P->n1, nh = P->nh;
-    const int npairs = (n0 + 1) / 2;
+    const int n1 = P->n1, nh = P->nh;
+    const int npairs = (nrows + 1) / 2;
     #pragma omp parallel
     {
-        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)(n1 > n0 ? n1 : n0));
-        offt_cpx* w = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)(n1 > n0 ? n1 : n0));
+        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n1);
+        offt_cpx* w = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n1);
         #pragma omp for schedule(static)
         for (int pr = 0; pr < npairs; ++pr) {
             const int ra = 2 * pr, rb = 2 * pr + 1;
-            const int paired = rb < n0;
+            const int paired = rb < nrows;
             for (int j = 0; j < n1; ++j) {
                 z[j].re = in[(size_t)ra * n1 + j];
                 z[j].im = paired ? in[(size_t)rb * n1 + j] : 0.0;
@@ -199,35 +202,33 @@ void offt_r2c_2d(const offt_plan2d* P, const double* in, offt_cpx* out)
                 }
             }
         }
-        #pragma omp for schedule(static)
-        for (int k = 0; k < nh; ++k) {
-            for (int r = 0; r < n0; ++r) z[r] = out[(size_t)r * nh + k];
-            const offt_cpx* Z = offt_exec1d(P->col, -1, z, w);
-            for (int r = 0; r < n0; ++r) out[(size_t)r * nh + k] = Z[r];
-        }
         free(z); free(w);
     }
 }
 
-void offt_c2r_2d(const offt_plan2d* P, const offt_cpx* in, double* out)
+/* One column transform of length n0, in place (sign -1 forward, +1 backward). */
+void offt_col(const offt_plan2d* P, int sign, offt_cpx* col)
 {
-    const int n0 = P->n0, n1 = P->n1, nh = P->nh;
-    const int npairs = (n0 + 1) / 2;
-    offt_cpx* H = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n0 * nh);
+    const int n0 = P->n0;
+    offt_cpx* w = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n0);
+    offt_cpx* Z = offt_exec1d(P->col, sign, col, w);
+    if (Z != col) memcpy(col, Z, sizeof(offt_cpx) * (size_t)n0);
+    free(w);
+}
+
+/* Row pass of the c2r transform on `nrows` consecutive rows: H[r][k] -> out[r][j]. */
+void offt_rows_inv(const offt_plan2d* P, const offt_cpx* H, int nrows, double* out)
+{
+    const int n1 = P->n1, nh = P->nh;
+    const int npairs = (nrows + 1) / 2;
     #pragma omp parallel
     {
-        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)(n1 > n0 ? n1 : n0));
-        offt_cpx* w = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)(n1 > n0 ? n1 : n0));
-        #pragma omp for schedule(static)
-        for (int k = 0; k < nh; ++k) {
-            for (int r = 0; r < n0; ++r) z[r] = in[(size_t)r * nh + k];
-            const offt_cpx* Z = offt_exec1d(P->col, +1, z, w);
-            for (int r = 0; r < n0; ++r) H[(size_t)r * nh + k] = Z[r];
-        }
+        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n1);
+        offt_cpx* w = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n1);
         #pragma omp for schedule(static)
         for (int pr = 0; pr < npairs; ++pr) {
             const int ra = 2 * pr, rb = 2 * pr + 1;
-            const int paired = rb < n0;
+            const int paired = rb < nrows;
             const offt_cpx* Ha = H + (size_t)ra * nh;
             const offt_cpx* Hb = H + (size_t)(paired ? rb : ra) * nh;
             for (int k = 0; k < nh; ++k) {
@@ -250,5 +251,40 @@ void offt_c2r_2d(const offt_plan2d* P, const offt_cpx* in, double* out)
         }
         free(z); free(w);
     }
+}
+
+void offt_r2c_2d(const offt_plan2d* P, const double* in, offt_cpx* out)
+{
+    const int n0 = P->n0, nh = P->nh;
+    offt_rows_fwd(P, in, n0, out);
+    #pragma omp parallel
+    {
+        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n0);
+        #pragma omp for schedule(static)
+        for (int k = 0; k < nh; ++k) {
+            for (int r = 0; r < n0; ++r) z[r] = out[(size_t)r * nh + k];
+            offt_col(P, -1, z);
+            for (int r = 0; r < n0; ++r) out[(size_t)r * nh + k] = z[r];
+        }
+        free(z);
+    }
+}
+
+void offt_c2r_2d(const offt_plan2d* P, const offt_cpx* in, double* out)
+{
+    const int n0 = P->n0, nh = P->nh;
+    offt_cpx* H = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n0 * nh);
+    #pragma omp parallel
+    {
+        offt_cpx* z = (offt_cpx*)malloc(sizeof(offt_cpx) * (size_t)n0);
+        #pragma omp for schedule(static)
+        for (int k = 0; k < nh; ++k) {
+            for (int r = 0; r < n0; ++r) z[r] = in[(size_t)r * nh + k];
+            offt_col(P, +1, z);
+            for (int r = 0; r < n0; ++r) H[(size_t)r * nh + k] = z[r];
+        }
+        free(z);
+    }
+    offt_rows_inv(P, H, n0, out);
     free(H);
 }

@@ -56,6 +56,10 @@ typedef struct offt_plan2d {
 offt_plan2d* offt_plan2d_create(int n0, int n1);
 void offt_plan2d_destroy(offt_plan2d* p);
 void offt_r2c_2d(const offt_plan2d* p, const double* in, offt_cpx* out);
+/* the separable pieces (row pass on a block of rows, one column transform in place) */
+void offt_rows_fwd(const offt_plan2d* p, const double* in, int nrows, offt_cpx* out);
+void offt_rows_inv(const offt_plan2d* p, const offt_cpx* H, int nrows, double* out);
+void offt_col(const offt_plan2d* p, int sign, offt_cpx* col);
 void offt_c2r_2d(const offt_plan2d* p, const offt_cpx* in, double* out);
 
 #ifdef __cplusplus

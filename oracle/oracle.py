@@ -79,6 +79,9 @@ def port_lib() -> C.CDLL:
         lib.offt_plan2d_destroy.argtypes = [C.c_void_p]
         lib.offt_r2c_2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.offt_c2r_2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.offt_rows_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.offt_rows_inv.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.offt_col.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.offt_factorize.argtypes = [C.c_int, C.POINTER(C.c_int)]
         lib.offt_factorize.restype = C.c_int
         _lib = lib
