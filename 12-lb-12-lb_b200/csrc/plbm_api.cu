@@ -361,7 +361,16 @@ int plbm_initialize(plbm_ctx* c)
 {
     if (!c) return fail("plbm_initialize: null context");
     if (!c->pop[0]) return fail("plbm_initialize: context was created with fields_only");
+    // the state of a freshly constructed LBmethod (reference src/plasma.cpp:58-124): initial populations,
+    // E = E_ext, phi = 0 and the Poisson module's call_once not yet taken
+    const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
     CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
+    CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
+    CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
+    c->poisson_called = false;
+    c->macro_valid = false;
     return 0;
 }
 

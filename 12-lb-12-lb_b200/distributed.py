@@ -167,6 +167,15 @@ class SlabDriver:
                     self._sendrecv(b.phi_last_row, b.phi_first_row, b.phi_below, b.phi_above)
                     b.poisson_stage(3)
 
+    def refresh_halos(self):
+        """Exchange the population halo rows of the current state (after an upload; plbm_initialize fills
+        them itself from the global initial condition, for which this is a no-op in effect)."""
+        b = self.b
+        with b.stream_context():
+            b.halo_pack()
+            self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi)
+            b.halo_unpack()
+
     def gather_fields(self, names):
         """All slabs' fields on every rank as full [NY, NX] arrays (tests, output)."""
         import torch
