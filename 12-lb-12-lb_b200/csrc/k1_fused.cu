@@ -25,10 +25,13 @@
 namespace plbm {
 
 #ifndef PLBM_K1_THREADS
-#define PLBM_K1_THREADS 128
+#define PLBM_K1_THREADS 64
+#endif
+#ifndef PLBM_K1_PAIR
+#define PLBM_K1_PAIR 1              // 1: both directions of an axis in one straight-line block
 #endif
 #ifndef PLBM_K1_MIN_BLOCKS
-#define PLBM_K1_MIN_BLOCKS 3
+#define PLBM_K1_MIN_BLOCKS 6
 #endif
 constexpr int K1_THREADS = PLBM_K1_THREADS;
 
@@ -87,30 +90,33 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
         D uE = D(0.0);
         if constexpr (s < 2) uE = vx[0] * Ex + vy[0] * Ey;                    // collisions.cpp:157,162
 
+        // Guo prefactor per weight class (4/9, 1/9, 1/36), collisions.cpp:154,159 -- three independent chains
+        D pref3[3] = { D(0.0), D(0.0), D(0.0) };
+        if constexpr (s < 2) {
+            #pragma unroll
+            for (int wc = 0; wc < 3; ++wc) pref3[wc] = guo_prefactor<s>(dv, wc, m.rho[s], c);
+        }
+
         #pragma unroll 1
         for (int axis = 0; axis < 5; ++axis) {
             const int wclass = (axis < 2) ? 1 : (axis < 4 ? 2 : 0);
+            const AxisSel sel = axis_select(axis);
             const D wr = D(c.w[wclass]) * m.rho[s];
             const D wT = D(c.w[wclass]) * m.T[s];
             BracketParts bp[3];
             #pragma unroll
-            for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot(axis, vx[j], vy[j]), c);
+            for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot(sel, vx[j], vy[j]), c);
             D pref = D(0.0), X = D(0.0), cE = D(0.0);
             if constexpr (s < 2) {
-                cE = axis_dot(axis, Ex, Ey);
-                pref = guo_prefactor<s>(dv, wclass, m.rho[s], c);
-                X = dv.cdiv(axis_dot(axis, vx[0], vy[0]) * cE, c.cs2);         // (c.u)(c.E)/cs2
+                cE = axis_dot(sel, Ex, Ey);
+                pref = (wclass == 1) ? pref3[1] : (wclass == 2 ? pref3[2] : pref3[0]);
+                X = dv.cdiv(bp[0].cu * cE, c.cs2);                             // (c.u)(c.E)/cs2
             }
-            const int nsign = (axis == 4) ? 1 : 2;
-            #pragma unroll 1
-            for (int sg = 0; sg < nsign; ++sg) {
-                const unsigned mask = sg ? 0x80000000u : 0u;
-                const int dir = (axis == 4) ? 0 : ((axis < 2 ? axis + 1 : axis + 3) + 2 * sg);
+            // one direction of this axis: mask 0 = the axis' first direction, 0x80000000 = its opposite
+            auto direction = [&](const unsigned mask, const int dir, const D fv, const D gv) {
                 D b[3];
                 #pragma unroll
                 for (int j = 0; j < 3; ++j) b[j] = bracket_value(bp[j], K[j], mask);
-                const D fv = D(stash[((s * 2 + 0) * NQ + dir) * K1_THREADS]);
-                const D gv = D(stash[((s * 2 + 1) * NQ + dir) * K1_THREADS]);
                 D force = D(0.0);
                 if constexpr (s < 2) force = pref * guo_bracket(X, cE, uE, mask);   // collisions.cpp:154-163
                 D fnew, gnew;
@@ -119,7 +125,28 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
                 dv.note_output(gnew);
                 o.dst[((s * 2 + 0) * NQ + dir) * o.plane] = fnew.v;
                 o.dst[((s * 2 + 1) * NQ + dir) * o.plane] = gnew.v;
+            };
+            const int d0 = (axis == 4) ? 0 : (axis < 2 ? axis + 1 : axis + 3);   // first direction of the axis; the opposite is d0 + 2
+#if PLBM_K1_PAIR
+            // both directions of the axis in one straight-line block: six independent division chains
+            const D f0 = D(stash[((s * 2 + 0) * NQ + d0) * K1_THREADS]), g0 = D(stash[((s * 2 + 1) * NQ + d0) * K1_THREADS]);
+            if (axis != 4) {
+                const D f1 = D(stash[((s * 2 + 0) * NQ + d0 + 2) * K1_THREADS]), g1 = D(stash[((s * 2 + 1) * NQ + d0 + 2) * K1_THREADS]);
+                direction(0u, d0, f0, g0);
+                direction(0x80000000u, d0 + 2, f1, g1);
+            } else {
+                direction(0u, d0, f0, g0);
             }
+#else
+            const int nsign = (axis == 4) ? 1 : 2;
+            #pragma unroll 1
+            for (int sg = 0; sg < nsign; ++sg) {
+                const int dir = d0 + 2 * sg;
+                const D fv = D(stash[((s * 2 + 0) * NQ + dir) * K1_THREADS]);
+                const D gv = D(stash[((s * 2 + 1) * NQ + dir) * K1_THREADS]);
+                direction(sg ? 0x80000000u : 0u, dir, fv, gv);
+            }
+#endif
         }
     });
 }

@@ -138,27 +138,38 @@ __device__ __forceinline__ VelSet make_velset(D vx, D vy, const LbmConsts& c)
     return v;
 }
 
-// c_i . v for the first direction of the axis (the second one is its negative):              (E1,E2)
+// c_i . v for the first direction of an axis (the second direction is its negative):            (E1,E2)
 //   axis 0: dirs (1,3) c=(1,0)   1: dirs (2,4) c=(0,1)   2: dirs (5,7) c=(1,1)   3: dirs (6,8) c=(-1,1)
 //   axis 4: the rest direction, c = 0
-__device__ __forceinline__ D axis_dot(int axis, D vx, D vy)
+// Branch-free: each component is kept, negated or replaced by +0 with integer masks (exact), then
+// one rounded addition -- exactly cx*vx + cy*vy of plasma.cpp:185-190 up to the sign of a zero.
+struct AxisSel {
+    unsigned keep_x, keep_y;   // 0xffffffff keeps the component, 0 replaces it by +0
+    unsigned flip_x;           // 0x80000000 negates vx (c_x = -1)
+};
+__device__ __forceinline__ AxisSel axis_select(int axis)
 {
-    switch (axis) {
-    case 0: return vx;
-    case 1: return vy;
-    case 2: return vx + vy;
-    case 3: return vy - vx;
-    default: return D(0.0);
-    }
+    AxisSel a;
+    a.keep_x = (axis == 0 || axis == 2 || axis == 3) ? 0xffffffffu : 0u;
+    a.keep_y = (axis >= 1 && axis <= 3) ? 0xffffffffu : 0u;
+    a.flip_x = (axis == 3) ? 0x80000000u : 0u;
+    return a;
+}
+__device__ __forceinline__ D axis_dot(const AxisSel& a, D vx, D vy)
+{
+    const double x = __hiloint2double((int)((((unsigned)__double2hiint(vx.v)) & a.keep_x) ^ a.flip_x), (int)(((unsigned)__double2loint(vx.v)) & a.keep_x));
+    const double y = __hiloint2double((int)(((unsigned)__double2hiint(vy.v)) & a.keep_y), (int)(((unsigned)__double2loint(vy.v)) & a.keep_y));
+    return D(x) + D(y);
 }
 
 // Sign-independent parts of the bracket 1 + cu*invcs2 + cu*cu*0.5*invcs2*invcs2 - K, plasma.cpp:196-200
 struct BracketParts {
-    D P, S;
+    D cu, P, S;
 };
 __device__ __forceinline__ BracketParts bracket_parts(D cu, const LbmConsts& c)
 {
     BracketParts b;
+    b.cu = cu;
     b.P = cu * D(c.invcs2);
     b.S = ((cu * cu) * D(c.hinvcs2)) * D(c.invcs2);                           // (E3)
     return b;
