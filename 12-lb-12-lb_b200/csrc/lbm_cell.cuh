@@ -35,9 +35,20 @@ __device__ __forceinline__ D div_tau(DV& dv, D x, const LbmConsts& c)
     if constexpr (TAU == 1) return x;
     else if constexpr (TAU == 2) return x * D(0.5);
     else if constexpr (TAU == 4) return x * D(0.25);
-    else if constexpr (TAU == 3) return dv.cdiv(x, c.tau3);
-    else if constexpr (TAU == 5) return dv.cdiv(x, c.tau5);
-    else { static_assert(TAU == 6, "unknown relaxation time"); return dv.cdiv(x, c.tau6); }
+    else if constexpr (TAU == 3) return dv.idiv(x, c.tau3, c.inv3);
+    else if constexpr (TAU == 5) return dv.idiv(x, c.tau5, c.inv5);
+    else { static_assert(TAU == 6, "unknown relaxation time"); return dv.idiv(x, c.tau6, c.inv6); }
+}
+
+// (18 * feq) / tau of collisions.cpp:86-96 (doubled, see E3).  For tau in {1,2,4} the quotient of the
+// rounded product by a power of two equals the single rounded product (18/tau) * feq.
+template <int TAU, class DV>
+__device__ __forceinline__ D c18_over_tau(DV& dv, D feq, const LbmConsts& c)
+{
+    if constexpr (TAU == 1) return D(18.0) * feq;
+    else if constexpr (TAU == 2) return D(9.0) * feq;
+    else if constexpr (TAU == 4) return D(4.5) * feq;
+    else return div_tau<TAU>(dv, D(18.0) * feq, c);
 }
 
 // Sums over the nine directions in the reference's i = 0..8 order, plasma.cpp:352-372.   (E1)
@@ -208,7 +219,7 @@ __device__ __forceinline__ void collide_species_dir(DV& dv, D fv, D gv, const D 
         constexpr int tau = TAU_VALUE[slot];
         feq[m] = wr * b[m];                                                   // plasma.cpp:195-249
         geq[m] = wT * b[m];                                                   // plasma.cpp:251-304
-        const D C18 = div_tau<tau>(dv, D(18.0) * feq[m], c);                  // 2 * (Q*feq/tau)          (E3)
+        const D C18 = c18_over_tau<tau>(dv, feq[m], c);                       // 2 * (Q*feq/tau)          (E3)
         q[m] = dv.xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                    // 2 * term_xy, collisions.cpp:86-96
         df[m] = div_tau<tau>(dv, fv - feq[m], c);                             // collisions.cpp:166-168
         dg[m] = div_tau<tau>(dv, gv - geq[m], c);                             // collisions.cpp:107-109

@@ -33,6 +33,9 @@ struct LbmConsts {
     Recip cs2;            // divisor cs2                     collisions.cpp:154-161
     Recip Kb;             // divisor Kb                      collisions.cpp:102-104
     Recip tau3, tau5, tau6;
+    // 1/tau for tau = 3, 5, 6 as an unevaluated sum hi + lo (hi = RN(1/tau), lo = RN(1/tau - hi)):
+    // x/tau == fma(hi, x, RN(lo*x)) for every normal-range x, see div_tau() in lbm_cell.cuh
+    double inv3[2], inv5[2], inv6[2];
     Recip m[2];           // m_e, m_i as divisors            plasma.cpp:389,409,452
     double hq[2];         // 0.5 * q_s                       plasma.cpp:389,409
     double q[2];          // q_e, q_i                        plasma.cpp:452

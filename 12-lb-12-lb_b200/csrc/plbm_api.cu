@@ -105,6 +105,15 @@ int build_consts(plbm_ctx* c)
         k.a2[slot] = 2.0 * k.a[slot];
         k.a4[slot] = 2.0 * k.a2[slot];
     }
+    {   // 1/tau = hi + lo: hi = RN(1/tau); 1 - hi*tau is exact in one fma, lo = RN((1 - hi*tau)/tau)
+        const double taus[3] = { 3.0, 5.0, 6.0 };
+        double* outs[3] = { k.inv3, k.inv5, k.inv6 };
+        for (int i = 0; i < 3; ++i) {
+            const double hi = 1.0 / taus[i];
+            outs[i][0] = hi;
+            outs[i][1] = std::fma(-hi, taus[i], 1.0) / taus[i];
+        }
+    }
     // refined reciprocals of the loop-invariant divisors, produced by the device itself
     const double div_h[7] = { cfg.cs2, cfg.Kb, 3.0, 5.0, 6.0, cfg.m[0], cfg.m[1] };
     double y_h[7];

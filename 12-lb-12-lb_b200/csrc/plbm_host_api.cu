@@ -2,11 +2,13 @@
 // Each call uploads its inputs, runs one kernel of phases.cu, and downloads the outputs.
 #include "../../include/plbm.h"
 
+#include <cmath>
 #include <cstdio>
 #include <string>
 #include <vector>
 
 #include "phases.h"
+#include "exact_math.cuh"
 
 using namespace plbm;
 
@@ -63,9 +65,55 @@ constexpr int EQ_SLOT[3][3] = { { 0, 3, 4 }, { 1, 6, 5 }, { 2, 7, 8 } };
 
 bool have_all(const double* const* p, int n) { for (int i = 0; i < n; ++i) if (!p || !p[i]) return false; return true; }
 
+// every fast division primitive on arbitrary operands, with its validity record
+__global__ void selftest_division_kernel(const double* a, const double* b, int n, int mode, double inv_hi, double inv_lo,
+                                         double recip_y, double* out, int* ok)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FastDiv dv;
+    D q;
+    const double inv[2] = { inv_hi, inv_lo };
+    Recip rc; rc.d = b[0]; rc.y = recip_y;
+    if (mode == 0) q = dv.xdiv(D(a[i]), D(b[i]));
+    else if (mode == 1) q = dv.idiv(D(a[i]), rc, inv);
+    else q = dv.cdiv(D(a[i]), rc);
+    dv.note_output(q);
+    out[i] = q.v;
+    ok[i] = dv.ok() ? 1 : 0;
+}
+__global__ void selftest_recip_kernel(const double* d, double* y) { y[0] = recip_refined(d[0]); }
+
 } // namespace
 
 extern "C" {
+
+int plbm_selftest_division(const double* a, const double* b, int n, int mode, double* out, int* ok)
+{
+    if (!a || !b || !out || !ok || n < 1) return plbm_set_error("plbm_selftest_division: bad argument");
+    Pool p;
+    double* da = p.up(a, n); double* db = p.up(b, mode == 0 ? n : 1); double* dout = p.alloc(n);
+    int* dok = nullptr;
+    if (p.err == cudaSuccess) p.err = cudaMalloc((void**)&dok, sizeof(int) * n);
+    if (dok) p.bufs.push_back(dok);
+    double* dy = p.alloc(1);
+    double y = 0.0, hi = 0.0, lo = 0.0;
+    if (mode != 0 && p.err == cudaSuccess) {
+        selftest_recip_kernel<<<1, 1>>>(db, dy);
+        p.down(&y, dy, 1);
+        hi = 1.0 / b[0];
+        lo = std::fma(-hi, b[0], 1.0) / b[0];
+    }
+    cudaError_t le = p.err;
+    if (le == cudaSuccess) {
+        selftest_division_kernel<<<(n + 255) / 256, 256>>>(da, db, n, mode, hi, lo, y, dout, dok);
+        le = cudaGetLastError();
+    }
+    if (finish(p, le, "plbm_selftest_division")) return 1;
+    p.down(out, dout, n);
+    if (p.err == cudaSuccess) p.err = cudaMemcpy(ok, dok, sizeof(int) * n, cudaMemcpyDeviceToHost);
+    return finish(p, cudaSuccess, "plbm_selftest_division");
+}
 
 int plbm_host_update_macro(int NX, int NY, const plbm_config* units, const double* const f[3], const double* const g[3],
                            const double* Ex, const double* Ey, double* const rho[3], double* const ux[3], double* const uy[3],

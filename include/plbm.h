@@ -162,6 +162,12 @@ int plbm_halo_unpack(plbm_ctx* ctx);
 int plbm_poisson_stage(plbm_ctx* ctx, int stage);
 int plbm_exchange_info(plbm_ctx* ctx, plbm_exchange* out);
 
+/* Self-test hook: the library's fast division primitives on caller-supplied operands.
+ * mode 0: a[i] / b[i] (data-dependent divisor); mode 1: a[i] / b[0] through the two-term 1/b[0] product (b[0] in {3,5,6});
+ * mode 2: a[i] / b[0] through the device-refined reciprocal.  ok[i] = 1 when the operands were inside the domain where the
+ * kernel accepts the fast result (otherwise the kernels recompute with IEEE division). */
+int plbm_selftest_division(const double* a, const double* b, int n, int mode, double* out, int* ok);
+
 /* Introspection used by the benchmarks and tests. */
 int plbm_local_rows(const plbm_ctx* ctx, int* y0, int* ny_local);
 long long plbm_device_bytes(const plbm_ctx* ctx);
