@@ -39,20 +39,22 @@ __device__ __forceinline__ cpx cmul(cpx a, cpx w)
     return { __dsub_rn(__dmul_rn(a.re, w.re), __dmul_rn(a.im, w.im)),
              __dadd_rn(__dmul_rn(a.re, w.im), __dmul_rn(a.im, w.re)) };
 }
-template <int SIGN>
+template <int SIGN, bool TW_SHARED = false>
 __device__ __forceinline__ cpx twiddle(const cpx* __restrict__ tw, int idx)
 {
+    const double2 t = TW_SHARED ? reinterpret_cast<const double2*>(tw)[idx]
+                                : __ldg(reinterpret_cast<const double2*>(tw) + idx);   // one 16-byte load
     cpx w;
-    w.re = __ldg(&tw[idx].re);
-    w.im = __ldg(&tw[idx].im);
-    if (SIGN > 0) w.im = -w.im;
+    w.re = t.x;
+    w.im = (SIGN > 0) ? -t.y : t.y;
     return w;
 }
 
 // In-place (single buffer) transform of buf[0..n).  All threads of the CTA must call it; on return
-// the result is in natural order and visible to every thread.
-template <int SIGN>
-__device__ void fft_smem(cpx* buf, const FftPlan& P)
+// the result is in natural order and visible to every thread.  EPT = elements per thread and stage
+// (a multiple of 4): the CTA must have at least ceil(n / EPT) threads.
+template <int SIGN, int EPT = FFT_MAX_EPT, bool TW_SHARED = false>
+__device__ __forceinline__ void fft_smem(cpx* buf, const FftPlan& P, const cpx* tw_table)
 {
     const int n = P.n;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -61,11 +63,11 @@ __device__ void fft_smem(cpx* buf, const FftPlan& P)
     for (int st = 0; st < P.nstages; ++st) {
         const int r = P.radix[st];
         const int m = nsub / r;
-        cpx out[FFT_MAX_EPT];
+        cpx out[EPT];
         if (r == 4) {
             const int nb = n >> 2;
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT / 4; ++e) {
+            for (int e = 0; e < EPT / 4; ++e) {
                 const int b = tid + e * nt;
                 if (b < nb) {
                     const int p = b / s, q = b - p * s;
@@ -83,16 +85,16 @@ __device__ void fft_smem(cpx* buf, const FftPlan& P)
                         b3 = { __dadd_rn(t1.re, t3.im), __dsub_rn(t1.im, t3.re) };
                     }
                     if (p != 0) {
-                        b1 = cmul(b1, twiddle<SIGN>(P.tw, p * s));
-                        b2 = cmul(b2, twiddle<SIGN>(P.tw, 2 * p * s));
-                        b3 = cmul(b3, twiddle<SIGN>(P.tw, 3 * p * s));
+                        b1 = cmul(b1, twiddle<SIGN, TW_SHARED>(tw_table, p * s));
+                        b2 = cmul(b2, twiddle<SIGN, TW_SHARED>(tw_table, 2 * p * s));
+                        b3 = cmul(b3, twiddle<SIGN, TW_SHARED>(tw_table, 3 * p * s));
                     }
                     out[4 * e + 0] = b0; out[4 * e + 1] = b1; out[4 * e + 2] = b2; out[4 * e + 3] = b3;
                 }
             }
             __syncthreads();
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT / 4; ++e) {
+            for (int e = 0; e < EPT / 4; ++e) {
                 const int b = tid + e * nt;
                 if (b < nb) {
                     const int p = b / s, q = b - p * s;
@@ -103,20 +105,20 @@ __device__ void fft_smem(cpx* buf, const FftPlan& P)
         } else if (r == 2) {
             const int nb = n >> 1;
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT / 2; ++e) {
+            for (int e = 0; e < EPT / 2; ++e) {
                 const int b = tid + e * nt;
                 if (b < nb) {
                     const int p = b / s, q = b - p * s;
                     const cpx a0 = buf[q + s * (p)];
                     const cpx a1 = buf[q + s * (p + m)];
                     cpx b1 = csub(a0, a1);
-                    if (p != 0) b1 = cmul(b1, twiddle<SIGN>(P.tw, p * s));
+                    if (p != 0) b1 = cmul(b1, twiddle<SIGN, TW_SHARED>(tw_table, p * s));
                     out[2 * e + 0] = cadd(a0, a1); out[2 * e + 1] = b1;
                 }
             }
             __syncthreads();
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT / 2; ++e) {
+            for (int e = 0; e < EPT / 2; ++e) {
                 const int b = tid + e * nt;
                 if (b < nb) {
                     const int p = b / s, q = b - p * s;
@@ -128,7 +130,7 @@ __device__ void fft_smem(cpx* buf, const FftPlan& P)
             // odd prime radix: every thread forms whole outputs, terms accumulated in k order
             const int step = n / r;   // w_r^e = W[e * n / r]
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT; ++e) {
+            for (int e = 0; e < EPT; ++e) {
                 const int o = tid + e * nt;
                 if (o < n) {
                     const int q = o % s;
@@ -138,15 +140,15 @@ __device__ void fft_smem(cpx* buf, const FftPlan& P)
                     for (int k = 1; k < r; ++k) {
                         const cpx ak = buf[q + s * (p + m * k)];
                         if (j == 0) acc = cadd(acc, ak);
-                        else acc = cadd(acc, cmul(ak, twiddle<SIGN>(P.tw, ((j * k) % r) * step)));
+                        else acc = cadd(acc, cmul(ak, twiddle<SIGN, TW_SHARED>(tw_table, ((j * k) % r) * step)));
                     }
-                    if (j != 0 && p != 0) acc = cmul(acc, twiddle<SIGN>(P.tw, j * p * s));
+                    if (j != 0 && p != 0) acc = cmul(acc, twiddle<SIGN, TW_SHARED>(tw_table, j * p * s));
                     out[e] = acc;
                 }
             }
             __syncthreads();
             #pragma unroll
-            for (int e = 0; e < FFT_MAX_EPT; ++e) {
+            for (int e = 0; e < EPT; ++e) {
                 const int o = tid + e * nt;
                 if (o < n) buf[o] = out[e];
             }

@@ -159,8 +159,14 @@ __device__ __noinline__ void k1_cell_exact(const double* stash, double Ex, doubl
     k1_cell<ExactDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), *o, *c);
 }
 
+#ifdef PLBM_K1_MAXNREG
+#define PLBM_K1_BOUNDS __maxnreg__(PLBM_K1_MAXNREG)
+#else
+#define PLBM_K1_BOUNDS __launch_bounds__(K1_THREADS, PLBM_K1_MIN_BLOCKS)
+#endif
+
 template <bool WRITE_MACRO>
-__global__ void __launch_bounds__(K1_THREADS, PLBM_K1_MIN_BLOCKS)
+__global__ void PLBM_K1_BOUNDS
 k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 const double* __restrict__ Exf, const double* __restrict__ Eyf,
                 double* __restrict__ rho_q, const MacroOut mo,
