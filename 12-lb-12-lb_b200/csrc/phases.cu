@@ -174,6 +174,51 @@ __global__ void stream_periodic_kernel(const double* __restrict__ s0, const doub
     d0[to] = s0[t]; d1[to] = s1[t]; d2[to] = s2[t];
 }
 
+// streaming.cpp:66-112 / :150-196 -- the reference's bounce-back push, restated per DESTINATION slot.
+// The reference's loop runs serially in (x outer, y, i) order and several sources can target one slot,
+// the last one winning; slots nobody targets keep what `dst` held before (stale temp_* contents).
+// A slot (X, Y, j) can be written by
+//   (1) plain streaming from (X - cx_j, Y - cy_j), direction j, when that cell exists;
+//   (2) a "y out only" reflection of direction o = opp(j) at cell (X + cx_j, Y): needs Y - cy_j outside;
+//   (3) an "x out only" reflection of direction o at cell (X, Y + cy_j): needs X - cx_j outside;
+//   (4) a corner reflection of direction o at (X, Y) itself: needs both outside.
+__constant__ int p_opp[NQ] = { 0, 3, 4, 1, 2, 7, 8, 5, 6 };
+
+__global__ void stream_bounceback_kernel(const double* __restrict__ s0, const double* __restrict__ s1, const double* __restrict__ s2,
+                                         double* __restrict__ d0, double* __restrict__ d1, double* __restrict__ d2, int NX, int NY)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NX * NY * NQ) return;
+    const int j = t % NQ, c = t / NQ, X = c % NX, Y = c / NX;
+    const int o = p_opp[j];
+    const bool xin = (X - p_cx[j] >= 0 && X - p_cx[j] < NX), yin = (Y - p_cy[j] >= 0 && Y - p_cy[j] < NY);
+    int bx = -1, by = -1, bi = -1;                       // winning source: the last in (x, y, i) order
+    auto offer = [&](int sx, int sy, int si) {
+        if (sx > bx || (sx == bx && (sy > by || (sy == by && si > bi)))) { bx = sx; by = sy; bi = si; }
+    };
+    if (xin && yin) offer(X - p_cx[j], Y - p_cy[j], j);                                  // (1)
+    if (!yin && X + p_cx[j] >= 0 && X + p_cx[j] < NX) offer(X + p_cx[j], Y, o);          // (2) source moves to x_str = X (inside), y_str outside
+    if (!xin && Y + p_cy[j] >= 0 && Y + p_cy[j] < NY) offer(X, Y + p_cy[j], o);          // (3)
+    if (!xin && !yin) offer(X, Y, o);                                                    // (4)
+    if (bi < 0) return;                                  // nobody writes this slot: it keeps its stale value
+    const size_t from = (size_t)bi + NQ * ((size_t)bx + (size_t)NX * by);
+    d0[t] = s0[from]; d1[t] = s1[from]; d2[t] = s2[from];
+}
+
+// LBmethod::Initialize in the host layout, plasma.cpp:131-158
+__global__ void init_aos_kernel(double* f0, double* f1, double* f2, double* g0, double* g1, double* g2, int NX, int NY,
+                                double r0, double r1, double r2, double T0, double T1, double T2)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= NX * NY * NQ) return;
+    const int i = t % NQ, c = t / NQ, x = c % NX, y = c / NX;
+    const double w = (i == 0) ? __ddiv_rn(4.0, 9.0) : (i < 5 ? __ddiv_rn(1.0, 9.0) : __ddiv_rn(1.0, 36.0));
+    const bool inside = (x >= NX / 4 + 1) && (x < 3 * NX / 4) && (y >= NY / 4 + 1) && (y < 3 * NY / 4);
+    f0[t] = inside ? __dmul_rn(w, r0) : 0.0; g0[t] = inside ? __dmul_rn(w, T0) : 0.0;
+    f1[t] = inside ? __dmul_rn(w, r1) : 0.0; g1[t] = inside ? __dmul_rn(w, T1) : 0.0;
+    f2[t] = __dmul_rn(w, r2);                g2[t] = __dmul_rn(w, T2);
+}
+
 static inline int blocks_for(long long n, int th) { return (int)((n + th - 1) / th); }
 
 cudaError_t launch_update_macro(const PhaseArrays& a, const PhaseUnits& u, int N, cudaStream_t s)
@@ -199,6 +244,18 @@ cudaError_t launch_collisions(const PhaseArrays& a, const PhaseUnits& u, int N, 
 cudaError_t launch_stream_periodic(const double* const src[3], double* const dst[3], int NX, int NY, cudaStream_t s)
 {
     stream_periodic_kernel<<<blocks_for((long long)NX * NY * NQ, 256), 256, 0, s>>>(src[0], src[1], src[2], dst[0], dst[1], dst[2], NX, NY);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_bounceback(const double* const src[3], double* const dst[3], int NX, int NY, cudaStream_t s)
+{
+    stream_bounceback_kernel<<<blocks_for((long long)NX * NY * NQ, 256), 256, 0, s>>>(src[0], src[1], src[2], dst[0], dst[1], dst[2], NX, NY);
+    return cudaGetLastError();
+}
+cudaError_t launch_init_aos(double* const f[3], double* const g[3], int NX, int NY, const double rho_init[3], const double T_init[3], cudaStream_t s)
+{
+    init_aos_kernel<<<blocks_for((long long)NX * NY * NQ, 256), 256, 0, s>>>(f[0], f[1], f[2], g[0], g[1], g[2], NX, NY,
+                                                                             rho_init[0], rho_init[1], rho_init[2], T_init[0], T_init[1], T_init[2]);
     return cudaGetLastError();
 }
 

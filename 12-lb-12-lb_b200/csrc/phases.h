@@ -24,5 +24,8 @@ cudaError_t launch_equilibrium(const PhaseArrays& a, const PhaseUnits& u, int N,
 cudaError_t launch_thermal_collisions(const PhaseArrays& a, const PhaseUnits& u, int N, cudaStream_t s);   // writes a.tmp
 cudaError_t launch_collisions(const PhaseArrays& a, const PhaseUnits& u, int N, cudaStream_t s);           // writes a.tmp
 cudaError_t launch_stream_periodic(const double* const src[3], double* const dst[3], int NX, int NY, cudaStream_t s);
+// bounce-back walls: dst must hold the stale contents the reference's temp_* arrays would hold
+cudaError_t launch_stream_bounceback(const double* const src[3], double* const dst[3], int NX, int NY, cudaStream_t s);
+cudaError_t launch_init_aos(double* const f[3], double* const g[3], int NX, int NY, const double rho_init[3], const double T_init[3], cudaStream_t s);
 
 } // namespace plbm

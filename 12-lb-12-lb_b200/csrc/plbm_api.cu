@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "exact_math.cuh"
@@ -17,7 +18,9 @@
 #include "k1_fused.h"
 #include "layout.h"
 #include "lbm_consts.h"
+#include "phases.h"
 #include "poisson_fft.h"
+#include "poisson_iter.h"
 
 using namespace plbm;
 
@@ -72,6 +75,13 @@ struct plbm_ctx {
     double* phi_below = nullptr; double* phi_above = nullptr;
     int slab_y0[PLBM_MAX_RANKS + 1] = {};
     int slab_k0[PLBM_MAX_RANKS + 1] = {};
+    // unfused device path (bounce-back walls): the reference's own array set in its own layout
+    bool unfused = false;
+    PhaseArrays pa = {};
+    PhaseUnits pu = {};
+    std::vector<double*> uf_bufs;
+    unsigned long long* err_bits = nullptr;  // iterative solvers: ping-pong max-update slots
+    int* iters_dev = nullptr;
     long long bytes = 0;
     std::vector<cudaEvent_t> events;
 };
@@ -203,7 +213,14 @@ int poisson_solver(plbm_ctx* c, int type, long long* launches)
         if (launches) *launches += 3;
         return 0;
     }
-    return fail("Poisson type %d is not built yet in this library", type);
+    if (type == PLBM_POISSON_GS || type == PLBM_POISSON_SOR || type == PLBM_POISSON_NPS) {
+        if (c->cfg.nranks != 1) return fail("the iterative Poisson solvers run on a single slab");
+        const int kind = (type == PLBM_POISSON_GS) ? 0 : (type == PLBM_POISSON_SOR ? 1 : 2);
+        CUDA_TRY(launch_poisson_iterative(kind, c->phi, c->rho_q, c->cfg.NX, c->cfg.NY, c->cfg.omega_sor, c->err_bits, c->iters_dev, c->stream));
+        if (launches) *launches += 1;
+        return 0;
+    }
+    return fail("unknown Poisson type %d", type);
 }
 
 // poisson::ComputeElectricField_Periodic / ComputeElectricField: phi -> Ex, Ey
@@ -216,7 +233,10 @@ int poisson_efield(plbm_ctx* c, int bc, long long* launches)
         if (launches) *launches += 1;
         return 0;
     }
-    return fail("field reconstruction with walls is not built yet in this library");
+    if (c->cfg.nranks != 1) return fail("field reconstruction with walls runs on a single slab");
+    CUDA_TRY(launch_efield_walls(c->phi, c->Ex, c->Ey, c->cfg.NX, c->cfg.NY, c->stream));
+    if (launches) *launches += 3;
+    return 0;
 }
 
 // poisson::SolvePoisson dispatch, reference src/poisson.cpp:25-82
@@ -232,6 +252,25 @@ int solve_poisson(plbm_ctx* c, long long* launches)
 
 int one_step(plbm_ctx* c, bool want_fields, long long* launches)
 {
+    if (c->unfused) {
+        // the reference's own sequence of sweeps (src/plasma.cpp:478-504) on its own array set; temp_* keeps the
+        // stale contents the bounce-back streaming lets through (src/streaming.cpp:66-112)
+        const int N = c->cfg.NX * c->cfg.NY;
+        PhaseArrays& a = c->pa;
+        CUDA_TRY(launch_update_macro(a, c->pu, N, c->stream));
+        CUDA_TRY(launch_equilibrium(a, c->pu, N, c->stream));
+        CUDA_TRY(launch_thermal_collisions(a, c->pu, N, c->stream));
+        for (int k = 0; k < 3; ++k) std::swap(a.g[k], a.tmp[k]);
+        CUDA_TRY(launch_collisions(a, c->pu, N, c->stream));
+        for (int k = 0; k < 3; ++k) std::swap(a.f[k], a.tmp[k]);
+        CUDA_TRY(launch_stream_bounceback(a.f, a.tmp, c->cfg.NX, c->cfg.NY, c->stream));
+        for (int k = 0; k < 3; ++k) std::swap(a.f[k], a.tmp[k]);
+        CUDA_TRY(launch_stream_bounceback(a.g, a.tmp, c->cfg.NX, c->cfg.NY, c->stream));
+        for (int k = 0; k < 3; ++k) std::swap(a.g[k], a.tmp[k]);
+        if (launches) *launches += 6;
+        c->macro_valid = true;
+        return 0;
+    }
     if (!c->pop[0]) return fail("plbm_step: context was created with fields_only");
     MacroOut mo;
     for (int s = 0; s < 3; ++s) {
@@ -285,7 +324,9 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     if ((long long)cfg->NX * cfg->NY * 9 >= (1LL << 31))
         return fail("plbm_create: NX*NY*9 must stay below 2^31 like the reference's int indices (reference src/plasma.cpp:58)");
     if (cfg->poisson_type < 0 || cfg->poisson_type > 4) return fail("plbm_create: unknown Poisson type %d", cfg->poisson_type);
-    if (cfg->bc_type != PLBM_BC_PERIODIC) return fail("plbm_create: boundary type %d is not built yet", cfg->bc_type);
+    if (cfg->bc_type != PLBM_BC_PERIODIC && cfg->bc_type != PLBM_BC_BOUNCEBACK) return fail("plbm_create: unknown boundary type %d", cfg->bc_type);
+    if (cfg->nranks > 1 && (cfg->bc_type != PLBM_BC_PERIODIC || (cfg->poisson_type != PLBM_POISSON_FFT && cfg->poisson_type != PLBM_POISSON_NONE)))
+        return fail("plbm_create: several slabs support periodic boundaries with the spectral (or no) Poisson solve only");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plbm_create: no CUDA device (this library has no CPU path)");
@@ -317,7 +358,8 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)cfg->NX * c->geom.NYl;
     const size_t pop_count = (size_t)NPLANES * c->geom.plane;
-    for (int b = 0; b < 2 && !cfg->fields_only; ++b) {
+    c->unfused = (cfg->bc_type == PLBM_BC_BOUNCEBACK) && !cfg->fields_only;
+    for (int b = 0; b < 2 && !cfg->fields_only && !c->unfused; ++b) {
         TRY_OR_DESTROY(dev_alloc(c, &c->pop[b], pop_count));
         CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
     }
@@ -326,7 +368,25 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     TRY_OR_DESTROY(dev_alloc(c, &c->rho_q, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->phi, n));
     for (int k = 0; k < 12 && !cfg->fields_only; ++k) TRY_OR_DESTROY(dev_alloc(c, &c->macro[k], n));
-    if (!cfg->fields_only) TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
+    if (!cfg->fields_only && !c->unfused) TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
+    TRY_OR_DESTROY(dev_alloc(c, &c->err_bits, 2));
+    TRY_OR_DESTROY(dev_alloc(c, &c->iters_dev, 1));
+    if (c->unfused) {
+        auto grab = [&](double** p, size_t count) -> int {
+            if (dev_alloc(c, p, count)) return 1;
+            c->uf_bufs.push_back(*p);
+            return cudaMemsetAsync(*p, 0, sizeof(double) * count, c->stream) == cudaSuccess ? 0 : fail("cudaMemsetAsync failed");
+        };
+        for (int k = 0; k < 3; ++k) {
+            TRY_OR_DESTROY(grab(&c->pa.f[k], n * NQ)); TRY_OR_DESTROY(grab(&c->pa.g[k], n * NQ)); TRY_OR_DESTROY(grab(&c->pa.tmp[k], n * NQ));
+            for (int m = 0; m < 3; ++m) { TRY_OR_DESTROY(grab(&c->pa.feq[k][m], n * NQ)); TRY_OR_DESTROY(grab(&c->pa.geq[k][m], n * NQ)); }
+            TRY_OR_DESTROY(grab(&c->pa.upx[k], n)); TRY_OR_DESTROY(grab(&c->pa.upy[k], n));
+            c->pa.ux[k] = c->macro[2 * k]; c->pa.uy[k] = c->macro[2 * k + 1]; c->pa.T[k] = c->macro[6 + k]; c->pa.rho[k] = c->macro[9 + k];
+        }
+        c->pa.Ex = c->Ex; c->pa.Ey = c->Ey; c->pa.rho_q = c->rho_q;
+        c->pu.cs2 = cfg->cs2; c->pu.Kb = cfg->Kb;
+        for (int k = 0; k < 3; ++k) { c->pu.q[k] = cfg->q[k]; c->pu.m[k] = cfg->m[k]; }
+    }
     CUDA_OR_DESTROY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
     CUDA_OR_DESTROY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
     CUDA_OR_DESTROY(launch_fill(c->Ex, cfg->Ex_ext, n, c->stream));        // reference src/plasma.cpp:116-117
@@ -357,6 +417,8 @@ void plbm_destroy(plbm_ctx* c)
     cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
     for (int k = 0; k < 12; ++k) cudaFree(c->macro[k]);
     cudaFree(c->staging);
+    for (double* p : c->uf_bufs) cudaFree(p);
+    cudaFree(c->err_bits); cudaFree(c->iters_dev);
     cudaFree(c->tw_row); cudaFree(c->tw_col); cudaFree(c->sx2); cudaFree(c->sy2);
     if (c->fft.T2 != c->fft.T1) cudaFree(c->fft.T2);
     cudaFree(c->fft.T1);
@@ -369,6 +431,18 @@ void plbm_destroy(plbm_ctx* c)
 int plbm_initialize(plbm_ctx* c)
 {
     if (!c) return fail("plbm_initialize: null context");
+    if (c->unfused) {
+        const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
+        CUDA_TRY(launch_init_aos(c->pa.f, c->pa.g, c->cfg.NX, c->cfg.NY, c->cfg.rho_init, c->cfg.T_init, c->stream));
+        for (int k = 0; k < 3; ++k) CUDA_TRY(cudaMemsetAsync(c->pa.tmp[k], 0, sizeof(double) * n * NQ, c->stream));   // std::vector::resize zero-fills temp_*
+        CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
+        CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
+        c->poisson_called = false;
+        c->macro_valid = false;
+        return 0;
+    }
     if (!c->pop[0]) return fail("plbm_initialize: context was created with fields_only");
     // the state of a freshly constructed LBmethod (reference src/plasma.cpp:58-124): initial populations,
     // E = E_ext, phi = 0 and the Poisson module's call_once not yet taken
@@ -386,6 +460,16 @@ int plbm_initialize(plbm_ctx* c)
 int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const g[3])
 {
     if (!c || !f || !g) return fail("plbm_upload_state: null argument");
+    if (c->unfused) {
+        const size_t ub = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
+        for (int s = 0; s < 3; ++s) {
+            if (!f[s] || !g[s]) return fail("plbm_upload_state: null array (species %d)", s);
+            CUDA_TRY(cudaMemcpyAsync(c->pa.f[s], f[s], ub, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->pa.g[s], g[s], ub, cudaMemcpyHostToDevice, c->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     if (!c->pop[0]) return fail("plbm_upload_state: context was created with fields_only");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
     for (int s = 0; s < 3; ++s)
@@ -402,6 +486,15 @@ int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const
 int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
 {
     if (!c || !f || !g) return fail("plbm_download_state: null argument");
+    if (c->unfused) {
+        const size_t ub = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
+        for (int s = 0; s < 3; ++s) {
+            if (f[s]) CUDA_TRY(cudaMemcpyAsync(f[s], c->pa.f[s], ub, cudaMemcpyDeviceToHost, c->stream));
+            if (g[s]) CUDA_TRY(cudaMemcpyAsync(g[s], c->pa.g[s], ub, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     if (!c->pop[0]) return fail("plbm_download_state: context was created with fields_only");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
     for (int s = 0; s < 3; ++s)

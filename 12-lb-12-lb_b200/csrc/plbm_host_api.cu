@@ -206,12 +206,14 @@ int plbm_host_collisions(int NX, int NY, const plbm_config* units, const double*
 int plbm_host_stream(int NX, int NY, int bc_type, const double* const in[3], double* const out[3])
 {
     if (!have_all(in, 3) || !have_all(out, 3)) return plbm_set_error("plbm_host_stream: null argument");
-    if (bc_type != PLBM_BC_PERIODIC) return plbm_set_error("plbm_host_stream: bounce-back streaming is not built yet in this library");
+    if (bc_type != PLBM_BC_PERIODIC && bc_type != PLBM_BC_BOUNCEBACK) return plbm_set_error("plbm_host_stream: unknown boundary type");
     const size_t n = (size_t)NX * NY * NQ;
     Pool p;
     const double* src[3]; double* dst[3];
-    for (int k = 0; k < 3; ++k) { src[k] = p.up(in[k], n); dst[k] = p.alloc(n); }
-    cudaError_t le = p.err == cudaSuccess ? launch_stream_periodic(src, dst, NX, NY, 0) : p.err;
+    // out[] is in-out: with walls, slots no source reaches keep what the caller's temp_* array held (reference quirk)
+    for (int k = 0; k < 3; ++k) { src[k] = p.up(in[k], n); dst[k] = p.up(out[k], n); }
+    cudaError_t le = p.err != cudaSuccess ? p.err
+                   : (bc_type == PLBM_BC_PERIODIC ? launch_stream_periodic(src, dst, NX, NY, 0) : launch_stream_bounceback(src, dst, NX, NY, 0));
     if (finish(p, le, "plbm_host_stream")) return 1;
     for (int k = 0; k < 3; ++k) p.down(out[k], dst[k], n);
     return finish(p, cudaSuccess, "plbm_host_stream");

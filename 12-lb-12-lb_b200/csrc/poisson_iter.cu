@@ -1,0 +1,139 @@
+// poisson_iter.cu -- the reference's iterative Poisson solvers and wall field reconstruction.
+//
+//   poisson::SolvePoisson_GS       /root/reference/src/poisson.cpp:90-142    red-black Gauss-Seidel
+//   poisson::SolvePoisson_SOR      /root/reference/src/poisson.cpp:216-279   red-black SOR
+//   poisson::SolvePoisson_9point   /root/reference/src/poisson.cpp:429-483   4-colour 9-point Gauss-Seidel
+//   poisson::ComputeElectricField  /root/reference/src/poisson.cpp:551-585   central differences + Neumann rim
+//
+// All three solvers sweep the interior 1..N-2 in place with phi = 0 on the rim, warm-started from
+// the previous step's phi, and stop after the FIRST iteration whose largest update is below 1e-8
+// (or after 5000 iterations).  Cells of one colour are independent, so a colour sweep is
+// order-independent and bit-reproducible; to stop at exactly the reference's iteration without a
+// host round trip per iteration, the whole solve is ONE cooperative kernel: grid-wide barriers
+// between colour sweeps, the iteration's maximum update reduced with warp shuffles and one
+// atomicMax per warp on the (non-negative) double's bit pattern.
+#include "poisson_iter.h"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace plbm {
+
+constexpr int ITER_MAX = 5000;        // poisson.cpp:13
+constexpr double ITER_TOL = 1e-8;     // poisson.cpp:14
+
+__device__ __forceinline__ double warp_max(double v)
+{
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// kind 0 = GS, 1 = SOR (5-point, 2 colours), 2 = 9-point (4 colours)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+poisson_iter_kernel(double* phi, const double* __restrict__ rho_q, int NX, int NY, double omega,
+                    unsigned long long* __restrict__ err_bits /* [2] ping-pong */, int* __restrict__ iters_out)
+{
+    cg::grid_group grid = cg::this_grid();
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    const int ix = NX - 2, iy = NY - 2;                       // interior extent
+    const long long ncell = (long long)(ix > 0 ? ix : 0) * (iy > 0 ? iy : 0);
+    constexpr int NCOL = (KIND == 2) ? 4 : 2;
+    int iter = 0;
+    for (; iter < ITER_MAX; ++iter) {
+        unsigned long long* slot = err_bits + (iter & 1);
+        double local = 0.0;
+        for (int colour = 0; colour < NCOL; ++colour) {
+            for (long long t = tid; t < ncell; t += nthreads) {
+                const int i = 1 + (int)(t % ix), j = 1 + (int)(t / ix);
+                const bool mine = (KIND == 2) ? ((2 * (i & 1) + (j & 1)) == colour) : (((i + j) & 1) == colour);
+                if (!mine) continue;
+                const size_t c = (size_t)i + (size_t)NX * j;
+                const double old = phi[c];
+                double nw;
+                if (KIND == 2) {                                                     // poisson.cpp:459-466
+                    const double so = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + 1], phi[c - 1]), phi[c + NX]), phi[c - NX]);
+                    const double sd = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + NX + 1], phi[c + NX - 1]), phi[c - NX + 1]), phi[c - NX - 1]);
+                    nw = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(4.0, so), sd), __dmul_rn(6.0, rho_q[c])), 20.0);
+                } else {                                                             // poisson.cpp:106-110, 231-241
+                    const double nb = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + 1], phi[c - 1]), phi[c + NX]), phi[c - NX]);
+                    const double gs = __dmul_rn(0.25, __dadd_rn(nb, rho_q[c]));
+                    nw = (KIND == 1) ? __dadd_rn(__dmul_rn(__dsub_rn(1.0, omega), old), __dmul_rn(omega, gs)) : gs;
+                }
+                phi[c] = nw;
+                local = fmax(local, fabs(__dsub_rn(nw, old)));
+            }
+            grid.sync();                                       // the next colour reads this colour's updates
+        }
+        local = warp_max(local);
+        if ((threadIdx.x & 31) == 0) atomicMax(slot, (unsigned long long)__double_as_longlong(local));
+        if (tid == 0) err_bits[(iter + 1) & 1] = 0ull;         // clear the other slot for the next iteration
+        grid.sync();
+        const double maxErr = __longlong_as_double((long long)*(volatile unsigned long long*)slot);
+        if (maxErr < ITER_TOL) { ++iter; break; }              // poisson.cpp:137-140, 275-277, 479-481
+    }
+    if (tid == 0 && iters_out) *iters_out = iter;
+}
+
+// poisson.cpp:556-563: interior central differences
+__global__ void efield_interior_kernel(const double* __restrict__ phi, double* __restrict__ Ex, double* __restrict__ Ey, int NX, int NY)
+{
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y;
+    if (i >= NX - 1 || j >= NY - 1) return;
+    const size_t c = (size_t)i + (size_t)NX * j;
+    Ex[c] = __dmul_rn(-0.5, __dsub_rn(phi[c + 1], phi[c - 1]));
+    Ey[c] = __dmul_rn(-0.5, __dsub_rn(phi[c + NX], phi[c - NX]));
+}
+// poisson.cpp:569-575: rows 0 and NY-1 copy rows 1 and NY-2 (all columns, stale corners included)
+__global__ void efield_rim_rows_kernel(double* __restrict__ Ex, double* __restrict__ Ey, int NX, int NY)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NX) return;
+    Ex[i] = Ex[(size_t)NX + i];                               Ey[i] = Ey[(size_t)NX + i];
+    Ex[(size_t)NX * (NY - 1) + i] = Ex[(size_t)NX * (NY - 2) + i]; Ey[(size_t)NX * (NY - 1) + i] = Ey[(size_t)NX * (NY - 2) + i];
+}
+// poisson.cpp:578-584: columns 0 and NX-1 copy columns 1 and NX-2 (all rows) -- runs after the rows
+__global__ void efield_rim_cols_kernel(double* __restrict__ Ex, double* __restrict__ Ey, int NX, int NY)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= NY) return;
+    const size_t r = (size_t)NX * j;
+    Ex[r] = Ex[r + 1];                 Ey[r] = Ey[r + 1];
+    Ex[r + NX - 1] = Ex[r + NX - 2];   Ey[r + NX - 1] = Ey[r + NX - 2];
+}
+
+cudaError_t launch_poisson_iterative(int kind, double* phi, const double* rho_q, int NX, int NY, double omega,
+                                     unsigned long long* err_bits, int* iters_out, cudaStream_t stream)
+{
+    void* fn = (kind == 0) ? (void*)poisson_iter_kernel<0> : (kind == 1) ? (void*)poisson_iter_kernel<1> : (void*)poisson_iter_kernel<2>;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0)) != cudaSuccess) return e;
+    const long long cells = (long long)(NX > 2 ? NX - 2 : 0) * (NY > 2 ? NY - 2 : 0);
+    long long want = (cells + 255) / 256;
+    if (want < 1) want = 1;
+    const long long cap = (long long)sms * (per_sm > 2 ? 2 : per_sm);    // resident by construction, few CTAs: cheap grid barriers
+    const int blocks = (int)(want < cap ? want : cap);
+    if ((e = cudaMemsetAsync(err_bits, 0, 2 * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    void* args[] = { &phi, &rho_q, &NX, &NY, &omega, &err_bits, &iters_out };
+    return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, stream);
+}
+
+cudaError_t launch_efield_walls(const double* phi, double* Ex, double* Ey, int NX, int NY, cudaStream_t stream)
+{
+    if (NX > 2 && NY > 2) {
+        dim3 grid((NX - 2 + 255) / 256, NY - 2);
+        efield_interior_kernel<<<grid, 256, 0, stream>>>(phi, Ex, Ey, NX, NY);
+    }
+    efield_rim_rows_kernel<<<(NX + 255) / 256, 256, 0, stream>>>(Ex, Ey, NX, NY);
+    efield_rim_cols_kernel<<<(NY + 255) / 256, 256, 0, stream>>>(Ex, Ey, NX, NY);
+    return cudaGetLastError();
+}
+
+} // namespace plbm

@@ -56,30 +56,32 @@ def run_driver(exe, args, dump_steps, NX, NY, cwd=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("NX,NY,steps,poisson", [(64, 64, 20, "fft"), (48, 40, 8, "none")])
-def test_lbmethod_run_simulation(oracle, plbm, NX, NY, steps, poisson):
+@pytest.mark.parametrize("NX,NY,steps,poisson,bc", [(64, 64, 20, "fft", "periodic"), (48, 40, 8, "none", "periodic"),
+                                                     (28, 28, 5, "sor", "bounceback"), (26, 30, 5, "nps", "periodic")])
+def test_lbmethod_run_simulation(oracle, plbm, NX, NY, steps, poisson, bc):
     build_drivers() if not (BUILD / "drive_lbmethod").exists() else None
     dumps = sorted({0, 1, steps - 1})
-    got = run_driver(BUILD / "drive_lbmethod", [NX, NY, steps, oracle.POISSON[poisson], 0], dumps, NX, NY)
-    o = oracle.PortOracle(NX, NY, poisson=poisson)
+    got = run_driver(BUILD / "drive_lbmethod", [NX, NY, steps, oracle.POISSON[poisson], oracle.BC[bc]], dumps, NX, NY)
+    o = oracle.PortOracle(NX, NY, poisson=poisson, bc=bc)
     want = o.run_with_dumps(steps, dumps)
     for t in dumps:
         for n in NAMES15:
-            assert_same_bits(got[t][n], want[t][n], f"LBmethod {NX}x{NY}/{poisson} step {t}: {n}")
+            assert_same_bits(got[t][n], want[t][n], f"LBmethod {NX}x{NY}/{poisson}/{bc} step {t}: {n}")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("NX,NY,steps,poisson", [(40, 40, 6, "fft"), (24, 36, 4, "none")])
-def test_free_functions_phase_by_phase(oracle, plbm, NX, NY, steps, poisson):
+@pytest.mark.parametrize("NX,NY,steps,poisson,bc", [(40, 40, 6, "fft", "periodic"), (24, 36, 4, "none", "periodic"),
+                                                     (22, 22, 4, "gs", "bounceback"), (24, 20, 4, "sor", "periodic")])
+def test_free_functions_phase_by_phase(oracle, plbm, NX, NY, steps, poisson, bc):
     """collisions::Collide, streaming::Stream, poisson::SolvePoisson on host vectors."""
     build_drivers() if not (BUILD / "drive_phases").exists() else None
     dumps = sorted({0, steps - 1})
-    got = run_driver(BUILD / "drive_phases", [NX, NY, steps, oracle.POISSON[poisson], 0], dumps, NX, NY)
-    o = oracle.PortOracle(NX, NY, poisson=poisson)
+    got = run_driver(BUILD / "drive_phases", [NX, NY, steps, oracle.POISSON[poisson], oracle.BC[bc]], dumps, NX, NY)
+    o = oracle.PortOracle(NX, NY, poisson=poisson, bc=bc)
     want = o.run_with_dumps(steps, dumps)
     for t in dumps:
         for n in NAMES15:
-            assert_same_bits(got[t][n], want[t][n], f"free functions {NX}x{NY}/{poisson} step {t}: {n}")
+            assert_same_bits(got[t][n], want[t][n], f"free functions {NX}x{NY}/{poisson}/{bc} step {t}: {n}")
 
 
 @pytest.mark.gpu

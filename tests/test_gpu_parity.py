@@ -120,3 +120,34 @@ def test_tiny_and_huge_values_take_the_exact_fallback(oracle, plbm):
             for s in range(3):
                 assert_same_bits(f3[s], o.f(s), f"extreme f[{s}]")
                 assert_same_bits(g3[s], o.g(s), f"extreme g[{s}]")
+
+
+@pytest.mark.parametrize("NX,NY,poisson,bc,nsteps", [
+    (24, 24, "sor", "bounceback", 6), (24, 24, "gs", "periodic", 6), (24, 24, "nps", "bounceback", 6),
+    (24, 24, "fft", "bounceback", 6), (30, 22, "none", "bounceback", 8), (32, 32, "sor", "periodic", 5),
+    (40, 40, "nps", "periodic", 4), (33, 27, "gs", "bounceback", 5),
+])
+def test_walls_and_iterative_solvers(oracle, plbm, NX, NY, poisson, bc, nsteps):
+    """bounce-back streaming with the reference's corner quirks (stale temp_* slots, last-writer-wins),
+    Dirichlet GS / SOR / 9-point solvers with warm start and the reference's exact stopping iteration, Neumann rim."""
+    run_both(oracle, plbm, NX, NY, poisson, nsteps, {0, 1, nsteps - 1}, bc=bc)
+
+
+@pytest.mark.parametrize("name", ["n24_sor_bounceback", "n24_gs_periodic", "n24_nps_bounceback", "n24_fft_bounceback",
+                                  "n32_fft_periodic", "n32_none_periodic", "n30x20_fft_periodic"])
+def test_against_golden_vectors_of_the_unmodified_reference(plbm, name):
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / f"{name}.npz")
+    NX, NY, steps = int(z["NX"]), int(z["NY"]), int(z["steps"])
+    dumps = [int(t) for t in z["dump_steps"]]
+    with plbm.PlasmaLBM(NX, NY, poisson=str(z["poisson"]), bc=str(z["bc"])) as sim:
+        for t in range(steps):
+            sim.step(1, want_fields=t in dumps)
+            if t in dumps:
+                got = sim.fields()
+                for fname in plbm.FIELD_NAMES:
+                    assert_same_bits(got[fname], z[f"t{t}_{fname}"], f"{name}: {fname} at step {t}")
+        f, g = sim.download_state()
+    for s in range(3):
+        assert_same_bits(f[s], z["pops_f"][s], f"{name}: f[{s}]")
+        assert_same_bits(g[s], z["pops_g"][s], f"{name}: g[{s}]")
