@@ -129,19 +129,27 @@ class SlabDriver:
         self.t1_splits = [2 * (k0[d + 1] - k0[d]) * nyl for d in range(self.nranks)]
         self.t2_splits = [2 * nkl * (y0[s + 1] - y0[s]) for s in range(self.nranks)]
 
-    def _sendrecv(self, send_up, send_down, recv_from_down, recv_from_up):
+    def _sendrecv(self, send_up, send_down, recv_from_down, recv_from_up, wait=True):
         """What I send up is what my upper neighbour receives from below, and vice versa.  With two
         slabs both neighbours are the same rank: the order send(up), send(down) / recv(down), recv(up)
-        pairs the messages correctly because point-to-point traffic between two ranks is ordered."""
+        pairs the messages correctly because point-to-point traffic between two ranks is ordered.
+        wait=False returns the pending work handles (the caller waits before it uses the buffers)."""
         d = self.dist
         ops = [d.P2POp(d.isend, send_up, self.up, self.group), d.P2POp(d.isend, send_down, self.down, self.group),
                d.P2POp(d.irecv, recv_from_down, self.down, self.group), d.P2POp(d.irecv, recv_from_up, self.up, self.group)]
-        for w in d.batch_isend_irecv(ops):
-            w.wait()
+        works = d.batch_isend_irecv(ops)
+        if wait:
+            for w in works:
+                w.wait()
+            return []
+        return works
 
     def step(self, nsteps: int = 1, want_fields: bool = False, timing=None):
         """nsteps time steps.  timing: optional list that receives one (start, end) CUDA event pair
-        around every fused collide-stream launch (CUDA backend only)."""
+        around every fused collide-stream launch (CUDA backend only).
+
+        Order inside a step: the population halo exchange only feeds the NEXT step's K1, so it is
+        started right after K1 and completed after the Poisson stages, which it overlaps."""
         b, d = self.b, self.dist
         with b.stream_context():
             for t in range(nsteps):
@@ -154,8 +162,7 @@ class SlabDriver:
                     timing.append((e0, e1))
                 # halo: top row's upward populations go up, bottom row's downward populations go down
                 b.halo_pack()
-                self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi)
-                b.halo_unpack()
+                pending = self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi, wait=False)
                 # spectral Poisson with two transposes
                 b.poisson_stage(0)
                 if b.has_poisson:
@@ -166,6 +173,9 @@ class SlabDriver:
                     # my top phi row is the row below my upper neighbour's slab, my bottom row the one above my lower neighbour's
                     self._sendrecv(b.phi_last_row, b.phi_first_row, b.phi_below, b.phi_above)
                     b.poisson_stage(3)
+                for w in pending:
+                    w.wait()
+                b.halo_unpack()
 
     def refresh_halos(self):
         """Exchange the population halo rows of the current state (after an upload; plbm_initialize fills
