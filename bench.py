@@ -275,8 +275,9 @@ E2E_WHAT = ("plbm_upload_state of the 6 AoS population arrays from pinned host m
             "LBmethod::Run_simulation hands them to the visualiser")
 
 # weak scaling: constant cells per GPU (2048^2) on square lattices of side ~ sqrt(N), like the reference's own weak-scaling
-# runs (build/weak_scalability.py); sides chosen with small prime factors for the spectral solve
-WEAK_SIDES = {1: 2048, 2: 2880, 4: 4096, 8: 5760}
+# runs (build/weak_scalability.py); sides of the form 2^k or 3*2^k keep the spectral solve on radix-4/2 stages (+ one radix-3),
+# so cells per GPU are 2048^2 (N=1,4) or 1.125 x 2048^2 (N=2,8)
+WEAK_SIDES = {1: 2048, 2: 3072, 4: 4096, 8: 6144}
 
 
 def base_line(args, nx, world, K, W, ms_total, mlups, cfg_name):
