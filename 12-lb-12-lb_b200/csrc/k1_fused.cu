@@ -17,10 +17,12 @@
 // thread, conflict-free).  The cell is then processed by k1_cell<FastDiv>: moments, then a ROLLED
 // loop over the five direction axes (two opposite directions each) so that the ~2.7 k FP64
 // instructions per cell come from a loop body that fits the instruction cache.  FastDiv records
-// whether every division stayed inside the domain where its 3/9-instruction sequence is exact;
-// if not (never on physical data), the cell is recomputed out of line with IEEE divisions.
+// whether every division stayed inside the domain where its 2/3/9-instruction sequence is exact;
+// if not (never on physical data), the cell is recomputed out of line with the reference's literal
+// arithmetic (literal_cell.cuh).
 #include "k1_fused.h"
 #include "lbm_cell.cuh"
+#include "literal_cell.cuh"
 
 namespace plbm {
 
@@ -151,12 +153,35 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
     });
 }
 
-// Out-of-line recomputation with IEEE divisions (operands outside FastDiv's proven domain).
+// Out-of-line recomputation of one cell with the reference's literal arithmetic (literal_cell.cuh): taken when the
+// validity record of the fast path trips (operands outside FastDiv's domain, non-finite values).
 template <bool WRITE_MACRO>
-__device__ __noinline__ void k1_cell_exact(const double* stash, double Ex, double Ey, const K1Out* o, const LbmConsts* c)
+__device__ __noinline__ void k1_cell_literal(const double* stash, double Ex, double Ey, const K1Out* o, const LbmConsts* c)
 {
-    ExactDiv dv;
-    k1_cell<ExactDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), *o, *c);
+    D f[3][NQ], g[3][NQ];
+    for (int s = 0; s < 3; ++s)
+        for (int i = 0; i < NQ; ++i) {
+            f[s][i] = D(stash[((s * 2 + 0) * NQ + i) * K1_THREADS]);
+            g[s][i] = D(stash[((s * 2 + 1) * NQ + i) * K1_THREADS]);
+        }
+    LitMacro m;
+    lit_update_macro(f, g, D(Ex), D(Ey), *c, m);
+    *o->rho_q = m.rho_q.v;
+    if (WRITE_MACRO) {
+        for (int s = 0; s < 3; ++s) {
+            o->mo.ux[s][o->cidx] = m.ux[s].v; o->mo.uy[s][o->cidx] = m.uy[s].v;
+            o->mo.T[s][o->cidx] = m.T[s].v;   o->mo.rho[s][o->cidx] = m.rho[s].v;
+        }
+    }
+    for (int i = 0; i < NQ; ++i) {
+        const D fi[3] = { f[0][i], f[1][i], f[2][i] }, gi[3] = { g[0][i], g[1][i], g[2][i] };
+        D fo[3], go[3];
+        lit_collide_direction(i, fi, gi, m, D(Ex), D(Ey), *c, fo, go);
+        for (int s = 0; s < 3; ++s) {
+            o->dst[((s * 2 + 0) * NQ + i) * o->plane] = fo[s].v;
+            o->dst[((s * 2 + 1) * NQ + i) * o->plane] = go[s].v;
+        }
+    }
 }
 
 #ifdef PLBM_K1_MAXNREG
@@ -190,6 +215,7 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
     const int r0o = (y + 1) * g.pitch, rmo = rm * g.pitch, rpo = rp * g.pitch;
     const int off[NQ] = { r0o + x, r0o + xm, rmo + x, r0o + xp, rpo + x, rmo + xm, rmo + xp, rpo + xp, rpo + xm };
 
+    unsigned nan_key = 0u;                             // max over the f inputs of 2*|high word|
     #pragma unroll
     for (int sk = 0; sk < 2 * NSPEC; ++sk) {
         const double* p = src + (long long)(sk * NQ) * g.plane;
@@ -198,6 +224,10 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
         for (int i = 0; i < NQ; ++i) v[i] = __ldg(p + i * g.plane + off[i]);
         #pragma unroll
         for (int i = 0; i < NQ; ++i) stash[(sk * NQ + i) * K1_THREADS] = v[i];
+        if ((sk & 1) == 0) {                           // f populations: remember whether any of them is a NaN
+            #pragma unroll
+            for (int i = 0; i < NQ; ++i) { const unsigned hi = (unsigned)__double2hiint(v[i]); nan_key = max(nan_key, hi + hi); }
+        }
     }
     const long long cidx = (long long)y * g.NX + x;    // scalar fields are flat x + NX*y
     const double Ex = __ldg(Exf + cidx), Ey = __ldg(Eyf + cidx);
@@ -211,7 +241,13 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
 
     FastDiv dv;
     k1_cell<FastDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), o, c);
-    if (!dv.ok()) k1_cell_exact<WRITE_MACRO>(stash, Ex, Ey, &o, &c);
+    // Outside FastDiv's domain the cell is redone with the literal arithmetic -- unless an f input is a (quiet) NaN and no tiny
+    // numerator was seen: then every population output and rho_q is NaN on either path (each species is coupled to both
+    // others through the pair velocities), and the only finite outputs, the moments of the NaN-free species, come from
+    // divisions by a density >= 1e-10 whose numerators the record covers.  This keeps a lattice that the reference's own
+    // dynamics have driven to NaN ("Divergence of the reference") at full speed.
+    const bool nan_input = nan_key > 0xffe00000u;
+    if (!dv.ok() && !(nan_input && dv.numerators_ok())) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, &o, &c);
 }
 
 static constexpr size_t k1_smem_bytes() { return sizeof(double) * NPLANES * K1_THREADS; }

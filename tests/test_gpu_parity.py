@@ -151,3 +151,33 @@ def test_against_golden_vectors_of_the_unmodified_reference(plbm, name):
     for s in range(3):
         assert_same_bits(f[s], z["pops_f"][s], f"{name}: f[{s}]")
         assert_same_bits(g[s], z["pops_g"][s], f"{name}: g[{s}]")
+
+
+def test_nan_and_inf_cells(oracle, plbm):
+    """Cells whose inputs already hold NaN / Inf (what the reference's own dynamics produce on large lattices):
+    NaN cells skip the IEEE fallback, Inf cells take it; either way the result equals the checker's, NaN for NaN."""
+    NX, NY = 64, 16
+    rng = np.random.default_rng(7)
+    f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9)); g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
+    f[2] *= 1e9
+    f[0][:, 0:8, 3] = np.nan          # electrons NaN in one direction
+    f[1][:, 8:16, 0] = np.inf         # ions Inf
+    f[2][:, 16:24, 5] = -np.inf
+    g[0][:, 24:32, 2] = np.nan        # NaN only in a thermal population
+    f[1][:, 32:40, :] = np.nan
+    f[0][:, 40:44, 1] = np.nan; f[1][:, 40:44, :] *= 1e-310   # NaN cell that ALSO has tiny numerators elsewhere
+    Ex = rng.normal(0, 1e-3, size=(NY, NX)); Ey = rng.normal(0, 1e-3, size=(NY, NX))
+    Ex[:, 48:52] = np.nan
+    o = oracle.PortOracle(NX, NY, poisson="none", initialize=False)
+    for s in range(3):
+        o.f(s)[...] = f[s]; o.g(s)[...] = g[s]
+    o.scalar(oracle.PO_EX)[...] = Ex; o.scalar(oracle.PO_EY)[...] = Ey
+    with plbm.PlasmaLBM(NX, NY, poisson="none", initialize=False) as sim:
+        sim.upload_state(f, g); sim.set_efield(Ex, Ey)
+        with np.errstate(all="ignore"):
+            for t in range(3):
+                o.step(1); sim.step(1, want_fields=True)
+                assert_fields_same(sim.fields(), o.fields(), f"nan/t={t}")
+            f3, g3 = sim.download_state()
+            for s in range(3):
+                assert_same_bits(f3[s], o.f(s), f"nan f[{s}]"); assert_same_bits(g3[s], o.g(s), f"nan g[{s}]")
