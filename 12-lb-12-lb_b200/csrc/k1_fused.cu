@@ -114,13 +114,14 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
                 pref = (wclass == 1) ? pref3[1] : (wclass == 2 ? pref3[2] : pref3[0]);
                 X = dv.cdiv(bp[0].cu * cE, c.cs2);                             // (c.u)(c.E)/cs2
             }
-            // one direction of this axis: mask 0 = the axis' first direction, 0x80000000 = its opposite
-            auto direction = [&](const unsigned mask, const int dir, const D fv, const D gv) {
+            // one direction of this axis: NEG = false is the axis' first direction, true its opposite
+            auto direction = [&](auto NEG, const int dir, const D fv, const D gv) {
+                constexpr bool neg = decltype(NEG)::value;
                 D b[3];
                 #pragma unroll
-                for (int j = 0; j < 3; ++j) b[j] = bracket_value(bp[j], K[j], mask);
+                for (int j = 0; j < 3; ++j) b[j] = bracket_value<neg>(bp[j], K[j]);
                 D force = D(0.0);
-                if constexpr (s < 2) force = pref * guo_bracket(X, cE, uE, mask);   // collisions.cpp:154-163
+                if constexpr (s < 2) force = pref * guo_bracket<neg>(X, cE, uE);   // collisions.cpp:154-163
                 D fnew, gnew;
                 collide_species_dir<s>(dv, fv, gv, b, wr, wT, AB2, rhoh, u2, force, c, fnew, gnew);
                 dv.note_output(fnew);
@@ -134,10 +135,10 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
             const D f0 = D(stash[((s * 2 + 0) * NQ + d0) * K1_THREADS]), g0 = D(stash[((s * 2 + 1) * NQ + d0) * K1_THREADS]);
             if (axis != 4) {
                 const D f1 = D(stash[((s * 2 + 0) * NQ + d0 + 2) * K1_THREADS]), g1 = D(stash[((s * 2 + 1) * NQ + d0 + 2) * K1_THREADS]);
-                direction(0u, d0, f0, g0);
-                direction(0x80000000u, d0 + 2, f1, g1);
+                direction(std::false_type{}, d0, f0, g0);
+                direction(std::true_type{}, d0 + 2, f1, g1);
             } else {
-                direction(0u, d0, f0, g0);
+                direction(std::false_type{}, d0, f0, g0);
             }
 #else
             const int nsign = (axis == 4) ? 1 : 2;
@@ -146,7 +147,8 @@ __device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash
                 const int dir = d0 + 2 * sg;
                 const D fv = D(stash[((s * 2 + 0) * NQ + dir) * K1_THREADS]);
                 const D gv = D(stash[((s * 2 + 1) * NQ + dir) * K1_THREADS]);
-                direction(sg ? 0x80000000u : 0u, dir, fv, gv);
+                if (sg) direction(std::true_type{}, dir, fv, gv);
+                else direction(std::false_type{}, dir, fv, gv);
             }
 #endif
         }

@@ -190,6 +190,13 @@ __device__ __forceinline__ D bracket_value(const BracketParts& b, D K, unsigned 
 {
     return ((D(1.0) + flip_sign(b.P, mask)) + b.S) - K;
 }
+// same with the direction's sign known at compile time: the negation rides on the DADD operand
+template <bool NEG>
+__device__ __forceinline__ D bracket_value(const BracketParts& b, D K)
+{
+    if constexpr (NEG) return ((D(1.0) - b.P) + b.S) - K;
+    else return ((D(1.0) + b.P) + b.S) - K;
+}
 
 // Per-cell, direction-independent part of the thermal source, collisions.cpp:86-96:
 // AB2 = 2*(2*rho*a*a - 2*a*rho) for the three relaxation times of species s.            (E3)
@@ -242,6 +249,12 @@ __device__ __forceinline__ D guo_prefactor(DV& dv, int wclass, D rho, const LbmC
 __device__ __forceinline__ D guo_bracket(D X, D cE, D uE, unsigned mask)
 {
     return (flip_sign(cE, mask) + X) - uE;
+}
+template <bool NEG>
+__device__ __forceinline__ D guo_bracket(D X, D cE, D uE)
+{
+    if constexpr (NEG) return (X - cE) - uE;      // (-cE) + X
+    else return (cE + X) - uE;
 }
 
 } // namespace plbm
