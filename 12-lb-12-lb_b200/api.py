@@ -71,6 +71,10 @@ def load_library() -> C.CDLL:
     lib.plbm_step.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.plbm_sync.argtypes = [C.c_void_p]
     lib.plbm_download_fields.argtypes = [C.c_void_p, C.POINTER(dp)]
+    lib.plbm_fetch_begin.argtypes = [C.c_void_p, C.POINTER(dp)]
+    lib.plbm_fetch_wait.argtypes = [C.c_void_p]
+    lib.plbm_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+    lib.plbm_unpin_host.argtypes = [C.c_void_p]
     lib.plbm_step_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.plbm_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -192,6 +196,23 @@ class PlasmaLBM:
         for k, n in enumerate(FIELD_NAMES):
             ptrs[k] = _dptr(out[n]) if n in out else dp()
         _check(self.lib, self.lib.plbm_download_fields(self._h, ptrs), "plbm_download_fields")
+        return out
+
+    def fetch_begin(self, out: np.ndarray, nfields: int = len(FIELD_NAMES)):
+        """Start copying the last step's first `nfields` fields into out[nfields, NY_local, NX] (ideally pinned memory)
+        and return at once; the next step() may be issued right away.  Complete it with fetch_wait()."""
+        if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or out.shape != (nfields, self.NY_local, self.NX):
+            raise ValueError("fetch_begin: out must be a C-contiguous float64 array [nfields, NY_local, NX]")
+        dp = C.POINTER(C.c_double)
+        ptrs = (dp * len(FIELD_NAMES))()
+        for k in range(len(FIELD_NAMES)):
+            ptrs[k] = _dptr(out[k]) if k < nfields else dp()
+        self._fetch_target = out                     # keep the destination alive until fetch_wait
+        _check(self.lib, self.lib.plbm_fetch_begin(self._h, ptrs), "plbm_fetch_begin")
+
+    def fetch_wait(self):
+        _check(self.lib, self.lib.plbm_fetch_wait(self._h), "plbm_fetch_wait")
+        out, self._fetch_target = getattr(self, "_fetch_target", None), None
         return out
 
     @property

@@ -63,7 +63,13 @@ struct plbm_ctx {
     double* pop[2] = { nullptr, nullptr };   // ping-pong population planes
     int cur = 0;                             // pop[cur] holds the current post-collision state
     double* Ex = nullptr; double* Ey = nullptr; double* rho_q = nullptr; double* phi = nullptr;
-    double* macro[12] = {};                  // ux,uy (e,i,n), T (e,i,n), rho (e,i,n) in plbm.h field order
+    double* macro[12] = {};                  // ux,uy (e,i,n), T (e,i,n), rho (e,i,n) in plbm.h field order (the set last written)
+    double* macro_sets[2][12] = {};          // fused path: alternating sets so that a pending fetch keeps its data
+    int macro_cur = 0;
+    double* snap[4] = {};                    // rho_q, Ex, Ey, phi as of the last plbm_fetch_begin
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_fetched = nullptr;
+    bool fetch_pending = false;
     double* staging = nullptr;               // 9*NX*NYl doubles for AoS transfers
     bool macro_valid = false;
     bool poisson_called = false;             // call_once of reference src/poisson.cpp:34-41
@@ -272,6 +278,10 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
         return 0;
     }
     if (!c->pop[0]) return fail("plbm_step: context was created with fields_only");
+    if (want_fields && c->macro_sets[1][0]) {              // fetch pipeline in use: write the set no pending copy reads
+        c->macro_cur ^= 1;
+        for (int k = 0; k < 12; ++k) c->macro[k] = c->macro_sets[c->macro_cur][k];
+    }
     MacroOut mo;
     for (int s = 0; s < 3; ++s) {
         mo.ux[s] = c->macro[2 * s]; mo.uy[s] = c->macro[2 * s + 1];
@@ -367,7 +377,10 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     TRY_OR_DESTROY(dev_alloc(c, &c->Ey, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->rho_q, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->phi, n));
-    for (int k = 0; k < 12 && !cfg->fields_only; ++k) TRY_OR_DESTROY(dev_alloc(c, &c->macro[k], n));
+    for (int k = 0; k < 12 && !cfg->fields_only; ++k) {
+        TRY_OR_DESTROY(dev_alloc(c, &c->macro_sets[0][k], n));
+        c->macro[k] = c->macro_sets[0][k];
+    }
     if (!cfg->fields_only && !c->unfused) TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
     TRY_OR_DESTROY(dev_alloc(c, &c->err_bits, 2));
     TRY_OR_DESTROY(dev_alloc(c, &c->iters_dev, 1));
@@ -415,7 +428,11 @@ void plbm_destroy(plbm_ctx* c)
     for (auto e : c->events) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) cudaFree(c->pop[b]);
     cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
-    for (int k = 0; k < 12; ++k) cudaFree(c->macro[k]);
+    for (int b = 0; b < 2; ++b) for (int k = 0; k < 12; ++k) cudaFree(c->macro_sets[b][k]);
+    for (int k = 0; k < 4; ++k) cudaFree(c->snap[k]);
+    if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+    if (c->ev_fetched) cudaEventDestroy(c->ev_fetched);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->staging);
     for (double* p : c->uf_bufs) cudaFree(p);
     cudaFree(c->err_bits); cudaFree(c->iters_dev);
@@ -553,6 +570,64 @@ int plbm_download_fields(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
         CUDA_TRY(cudaMemcpyAsync(out[k], src, bytes, cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
+{
+    if (!c || !out) return fail("plbm_fetch_begin: null argument");
+    if (c->fetch_pending) return fail("plbm_fetch_begin: the previous fetch was not completed with plbm_fetch_wait");
+    const size_t n = (size_t)c->geom.NX * c->geom.NYl, bytes = sizeof(double) * n;
+    if (!c->copy_stream) {                                 // first use: second macro set, snapshot buffers, copy stream
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k) if (dev_alloc(c, &c->snap[k], n)) return 1;
+        if (!c->unfused && !c->cfg.fields_only) {
+            c->macro_cur = 0;
+            for (int k = 0; k < 12; ++k) if (dev_alloc(c, &c->macro_sets[1][k], n)) return 1;
+        }
+    }
+    bool any_macro = false;
+    for (int k = 0; k < 12; ++k) any_macro |= (out[k] != nullptr);
+    if (any_macro && !c->macro_valid) return fail("plbm_fetch_begin: moment fields were not requested from the last plbm_step");
+    // rho_q / E / phi are overwritten by the next step: snapshot them on the compute stream (device copies)
+    const double* live[4] = { c->rho_q, c->Ex, c->Ey, c->phi };
+    for (int k = 0; k < 4; ++k)
+        if (out[12 + k]) CUDA_TRY(cudaMemcpyAsync(c->snap[k], live[k], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_snap, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    for (int k = 0; k < PLBM_NUM_FIELDS; ++k) {
+        if (!out[k]) continue;
+        const double* src = (k < 12) ? c->macro[k] : c->snap[k - 12];
+        CUDA_TRY(cudaMemcpyAsync(out[k], src, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_fetched, c->copy_stream));
+    if (c->unfused && any_macro)                           // single moment set on this path: the next sweep waits for the copy
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_fetched, 0));
+    c->fetch_pending = true;
+    return 0;
+}
+
+int plbm_pin_host(void* p, size_t bytes)
+{
+    if (!p || !bytes) return fail("plbm_pin_host: empty range");
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+int plbm_unpin_host(void* p)
+{
+    if (!p) return 0;
+    CUDA_TRY(cudaHostUnregister(p));
+    return 0;
+}
+
+int plbm_fetch_wait(plbm_ctx* c)
+{
+    if (!c) return fail("plbm_fetch_wait: null context");
+    if (!c->fetch_pending) return 0;
+    CUDA_TRY(cudaEventSynchronize(c->ev_fetched));
+    c->fetch_pending = false;
     return 0;
 }
 

@@ -36,7 +36,29 @@ LBmethod::LBmethod(const int _NSTEPS, const int _NX, const int _NY, const size_t
     for (auto& f : fields_) f.assign(n, 0.0);
 }
 
-LBmethod::~LBmethod() { plbm_destroy(ctx_); }
+LBmethod::~LBmethod()
+{
+    if (ctx_) plbm_fetch_wait(ctx_);
+    if (pinned_) {
+        for (auto& f : fields_) plbm_unpin_host(f.data());
+        for (auto& f : inflight_) plbm_unpin_host(f.data());
+    }
+    plbm_destroy(ctx_);
+}
+
+// Run_simulation hands every step's 15 fields to the visualiser: the copy of step t+1 runs on the library's copy
+// stream into inflight_ while the device already computes and the host draws step t from fields_.
+void LBmethod::begin_fetch()
+{
+    double* out[PLBM_NUM_FIELDS] = {};
+    for (int k = 0; k < 15; ++k) out[k] = inflight_[k].data();
+    if (plbm_fetch_begin(ctx_, out)) raise("LBmethod: field fetch");
+}
+void LBmethod::finish_fetch()
+{
+    if (plbm_fetch_wait(ctx_)) raise("LBmethod: field fetch");
+    for (int k = 0; k < 15; ++k) fields_[k].swap(inflight_[k]);
+}
 
 void LBmethod::fetch_fields()
 {
@@ -63,8 +85,23 @@ void LBmethod::Step(int nsteps, bool want_fields)
 void LBmethod::Run_simulation()
 {
     visualize::InitVisualization(NX, NY, NSTEPS);
+    if (!pinned_) {                                           // page-lock both field sets once (best effort)
+        const size_t bytes = sizeof(double) * static_cast<size_t>(NX) * NY;
+        for (auto& f : inflight_) f.assign(static_cast<size_t>(NX) * NY, 0.0);
+        pinned_ = true;
+        for (auto& f : fields_) pinned_ = pinned_ && plbm_pin_host(f.data(), bytes) == 0;
+        for (auto& f : inflight_) pinned_ = pinned_ && plbm_pin_host(f.data(), bytes) == 0;
+    }
+    if (NSTEPS > 0) {
+        if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+        begin_fetch();
+    }
     for (int t = 0; t < NSTEPS; ++t) {
-        Step(1, true);
+        finish_fetch();                                       // fields_ = step t
+        if (t + 1 < NSTEPS) {
+            if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+            begin_fetch();
+        }
         visualize::UpdateVisualization(t, NX, NY,
                                        fields_[PLBM_F_UX_E], fields_[PLBM_F_UY_E],
                                        fields_[PLBM_F_UX_I], fields_[PLBM_F_UY_I],

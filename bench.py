@@ -12,7 +12,7 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      K1 (fused collide-stream) against the measured HBM copy peak; 888 algorithmic B/update
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/ref_plasma_timing) on the host cores, bounded sample
   e2e           same metric through the public API with HOST buffers: initial state uploaded from pinned
-                memory, the 15 visualised fields + phi downloaded to pinned memory every step
+                memory, the 15 visualised fields fetched to pinned memory every step (copy of step t overlapped with step t+1)
 """
 from __future__ import annotations
 
@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=0, help="lattice side (default: 2048 at N=1)")
     ap.add_argument("--poisson", default="fft")
     ap.add_argument("--cpu-steps", type=int, default=4, help="time steps of the CPU baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -216,7 +216,8 @@ def main():
         Ke = max(1, min(args.e2e_steps, K))
         f_host = torch.empty((3, nx, nx, 9), dtype=torch.float64).pin_memory()
         g_host = torch.empty((3, nx, nx, 9), dtype=torch.float64).pin_memory()
-        out_host = torch.empty((len(P.FIELD_NAMES), nx, nx), dtype=torch.float64).pin_memory()
+        NF = 15                                   # what visualize::UpdateVisualization takes (phi is not part of it)
+        out_host = [torch.empty((NF, nx, nx), dtype=torch.float64).pin_memory() for _ in range(2)]
         sim.initialize()                          # e2e starts from the reference's initial condition as well
         f0, g0 = sim.download_state()
         f_host.numpy()[...] = f0
@@ -226,19 +227,24 @@ def main():
         dp = C.POINTER(C.c_double)
         fa = (dp * 3)(*[C.cast(f_host[s].data_ptr(), dp) for s in range(3)])
         ga = (dp * 3)(*[C.cast(g_host[s].data_ptr(), dp) for s in range(3)])
-        outs = (dp * len(P.FIELD_NAMES))(*[C.cast(out_host[k].data_ptr(), dp) for k in range(len(P.FIELD_NAMES))])
+        outs = [(dp * len(P.FIELD_NAMES))(*([C.cast(o[k].data_ptr(), dp) for k in range(NF)] + [dp()] * (len(P.FIELD_NAMES) - NF)))
+                for o in out_host]
         lib = sim.lib
         sim.sync()
         t0 = time.perf_counter()
         if lib.plbm_upload_state(sim._h, fa, ga) != 0:
             raise SystemExit(lib.plbm_last_error().decode())
-        for _ in range(Ke):
-            if lib.plbm_step(sim._h, 1, 1) != 0 or lib.plbm_download_fields(sim._h, outs) != 0:
+        # LBmethod::Run_simulation's loop (12-lb-12-lb_b200/host/plasma.cpp): step t+1 is issued while step t's fields
+        # are still crossing PCIe; every step's 15 fields are complete in host memory before the next fetch is started
+        for k in range(Ke):
+            if lib.plbm_step(sim._h, 1, 1) != 0 or lib.plbm_fetch_wait(sim._h) != 0 or lib.plbm_fetch_begin(sim._h, outs[k & 1]) != 0:
                 raise SystemExit(lib.plbm_last_error().decode())
+        if lib.plbm_fetch_wait(sim._h) != 0:
+            raise SystemExit(lib.plbm_last_error().decode())
         sim.sync()
         dt = time.perf_counter() - t0
         line["e2e"] = {"value": cells * Ke / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 6 * 9 * cells * 8 / Ke,
-                       "d2h_bytes_per_step": len(P.FIELD_NAMES) * cells * 8, "steps": Ke, "what": E2E_WHAT}
+                       "d2h_bytes_per_step": NF * cells * 8, "steps": Ke, "what": E2E_WHAT}
         del f_host, g_host, out_host
 
     # ---- cpu baseline (bounded sample of the same workload) -------------------------------
@@ -271,8 +277,8 @@ def segments(K):
 
 
 E2E_WHAT = ("plbm_upload_state of the 6 AoS population arrays from pinned host memory (once, amortised over the steps), then per "
-            "step the time step + plbm_download_fields of the 15 visualised fields + phi into pinned host memory, as "
-            "LBmethod::Run_simulation hands them to the visualiser")
+            "step the time step + plbm_fetch_begin/plbm_fetch_wait of the 15 visualised fields into pinned host memory, as "
+            "LBmethod::Run_simulation hands them to the visualiser (the copy of step t overlaps the kernels of step t+1)")
 
 # weak scaling: constant cells per GPU (2048^2) on square lattices of side ~ sqrt(N), like the reference's own weak-scaling
 # runs (build/weak_scalability.py); sides of the form 2^k or 3*2^k keep the spectral solve on radix-4/2 stages (+ one radix-3),
@@ -348,22 +354,26 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
         import ctypes as C
         Ke = max(1, min(args.e2e_steps, K))
         nyl = b.slab_y0[rank + 1] - b.slab_y0[rank]
-        out_host = torch.empty((len(P.FIELD_NAMES), nyl, nx), dtype=torch.float64).pin_memory()
+        NF = 15
+        out_host = [torch.empty((NF, nyl, nx), dtype=torch.float64).pin_memory() for _ in range(2)]
         dp = C.POINTER(C.c_double)
-        outs = (dp * len(P.FIELD_NAMES))(*[C.cast(out_host[k].data_ptr(), dp) for k in range(len(P.FIELD_NAMES))])
+        outs = [(dp * len(P.FIELD_NAMES))(*([C.cast(o[k].data_ptr(), dp) for k in range(NF)] + [dp()] * (len(P.FIELD_NAMES) - NF)))
+                for o in out_host]
         b.sync(); dist.barrier()
         t0 = time.perf_counter()
-        for _ in range(Ke):
+        for k in range(Ke):
             drv.step(1, want_fields=True)
-            if b.lib.plbm_download_fields(b.sim._h, outs) != 0:
+            if b.lib.plbm_fetch_wait(b.sim._h) != 0 or b.lib.plbm_fetch_begin(b.sim._h, outs[k & 1]) != 0:
                 raise SystemExit(b.lib.plbm_last_error().decode())
+        if b.lib.plbm_fetch_wait(b.sim._h) != 0:
+            raise SystemExit(b.lib.plbm_last_error().decode())
         b.sync(); dist.barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": cells * Ke / float(dt.item()) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0,
-                       "d2h_bytes_per_step": len(P.FIELD_NAMES) * cells * 8, "steps": Ke,
+                       "d2h_bytes_per_step": NF * cells * 8, "steps": Ke,
                        "what": "initial state built on the device (plbm_initialize); per step the time step + download of every slab's 15 "
-                               "visualised fields + phi into pinned host memory (all ranks in parallel)"}
+                               "visualised fields into pinned host memory (all ranks in parallel)"}
     b.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -49,5 +49,9 @@ private:
     const size_t n_cores;
     plbm_ctx* ctx_ = nullptr;
     std::vector<double> fields_[15];                          // order of visualize::UpdateVisualization
+    std::vector<double> inflight_[15];                        // Run_simulation: the step being copied while fields_ is drawn
+    bool pinned_ = false;
+    void begin_fetch();
+    void finish_fetch();
     void fetch_fields();
 };

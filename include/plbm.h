@@ -91,6 +91,20 @@ int plbm_sync(plbm_ctx* ctx);
  * out[k] == NULL skips field k.  Synchronises. */
 int plbm_download_fields(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
 
+/* Pipelined variant of plbm_download_fields for loops that hand every step's fields to a consumer
+ * (LBmethod::Run_simulation -> visualize::UpdateVisualization): plbm_fetch_begin starts copying the fields of
+ * the LAST step into out[] on a separate copy stream and returns at once; the next plbm_step may be issued
+ * immediately and overlaps the transfer (the library keeps the data of the pending fetch intact: alternating
+ * moment buffers, device snapshots of rho_q / E / phi).  plbm_fetch_wait blocks until out[] is complete.
+ * out[] should be page-locked (cudaHostRegister / pinned) for the copy to be asynchronous.  At most one fetch
+ * may be pending. */
+int plbm_fetch_begin(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
+int plbm_fetch_wait(plbm_ctx* ctx);
+/* Page-lock / release a host range owned by the caller (cudaHostRegister) so that plbm_fetch_begin, plbm_upload_state
+ * and plbm_download_* move it at full PCIe rate and asynchronously.  Optional: unpinned memory stays correct. */
+int plbm_pin_host(void* p, size_t bytes);
+int plbm_unpin_host(void* p);
+
 /* Same as plbm_step but timed with CUDA events on the library's stream.  Any of the outputs may
  * be NULL.  ms_k1 / ms_poisson are the summed durations of the fused collide-stream kernel and of
  * the Poisson + field kernels; launches = number of kernels launched. */

@@ -181,3 +181,30 @@ def test_nan_and_inf_cells(oracle, plbm):
             f3, g3 = sim.download_state()
             for s in range(3):
                 assert_same_bits(f3[s], o.f(s), f"nan f[{s}]"); assert_same_bits(g3[s], o.g(s), f"nan g[{s}]")
+
+
+@pytest.mark.parametrize("poisson,bc", [("fft", "periodic"), ("sor", "bounceback")])
+def test_pipelined_fetch_delivers_every_step(oracle, plbm, poisson, bc):
+    """plbm_fetch_begin / plbm_fetch_wait (LBmethod::Run_simulation's loop): the copy of step t is pending while
+    step t+1 already runs, and must still deliver step t's fields -- all 16, every step."""
+    NX = NY = 48
+    nsteps = 9
+    o = oracle.PortOracle(NX, NY, poisson=poisson, bc=bc)
+    bufs = [np.full((16, NY, NX), np.nan), np.full((16, NY, NX), np.nan)]
+    with plbm.PlasmaLBM(NX, NY, poisson=poisson, bc=bc) as sim:
+        sim.step(1, want_fields=True)
+        sim.fetch_begin(bufs[0])
+        for t in range(nsteps):
+            if t + 1 < nsteps:
+                sim.step(1, want_fields=True)            # issued while the fetch of step t is pending
+            got = sim.fetch_wait()
+            assert got is bufs[t & 1]
+            if t + 1 < nsteps:
+                sim.fetch_begin(bufs[(t + 1) & 1])
+            o.step(1)
+            assert_fields_same({n: got[k] for k, n in enumerate(plbm.FIELD_NAMES)}, o.fields(), f"pipelined {poisson}/{bc} t={t}")
+        sim.fetch_begin(bufs[0])
+        with pytest.raises(plbm.PlbmError):
+            sim.fetch_begin(bufs[1])                     # a second fetch before fetch_wait is refused
+        sim.fetch_wait()
+    o.close()
