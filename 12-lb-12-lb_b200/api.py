@@ -75,6 +75,7 @@ def load_library() -> C.CDLL:
     lib.plbm_fetch_wait.argtypes = [C.c_void_p]
     lib.plbm_pin_host.argtypes = [C.c_void_p, C.c_size_t]
     lib.plbm_unpin_host.argtypes = [C.c_void_p]
+    lib.plbm_host_solve_poisson.argtypes = [C.c_void_p, dp, dp, dp]
     lib.plbm_step_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.plbm_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -110,9 +111,10 @@ class PlasmaLBM:
 
     def __init__(self, NX: int, NY: int, poisson: str = "fft", bc: str = "periodic", omega: float = 1.8,
                  rank: int = 0, nranks: int = 1, y0: int = 0, NY_local: int | None = None, device: int = -1,
-                 initialize: bool = True, **si):
+                 initialize: bool = True, fields_only: bool = False, **si):
         self.lib = load_library()
         cfg = PlbmConfig()
+        cfg.fields_only = 1 if fields_only else 0
         cfg.NX, cfg.NY = NX, NY
         cfg.poisson_type, cfg.bc_type, cfg.omega_sor = POISSON[poisson], BC[bc], omega
         cfg.rank, cfg.nranks, cfg.y0 = rank, nranks, y0
@@ -126,7 +128,7 @@ class PlasmaLBM:
         y0_, nyl = C.c_int(), C.c_int()
         self.lib.plbm_local_rows(self._h, C.byref(y0_), C.byref(nyl))
         self.y0, self.NY_local = y0_.value, nyl.value
-        if initialize:
+        if initialize and not fields_only:
             self.initialize()
 
     def close(self):
@@ -197,6 +199,15 @@ class PlasmaLBM:
             ptrs[k] = _dptr(out[n]) if n in out else dp()
         _check(self.lib, self.lib.plbm_download_fields(self._h, ptrs), "plbm_download_fields")
         return out
+
+    def solve_poisson(self, rho_q, Ex=None, Ey=None):
+        """poisson::SolvePoisson on host arrays (plbm_host_solve_poisson): returns (Ex, Ey); the potential stays in the
+        context (fields(["phi"]))."""
+        rho_q = np.ascontiguousarray(rho_q, dtype=np.float64)
+        Ex = np.zeros_like(rho_q) if Ex is None else np.ascontiguousarray(Ex, dtype=np.float64).copy()
+        Ey = np.zeros_like(rho_q) if Ey is None else np.ascontiguousarray(Ey, dtype=np.float64).copy()
+        _check(self.lib, self.lib.plbm_host_solve_poisson(self._h, _dptr(rho_q), _dptr(Ex), _dptr(Ey)), "plbm_host_solve_poisson")
+        return Ex, Ey
 
     def fetch_begin(self, out: np.ndarray, nfields: int = len(FIELD_NAMES)):
         """Start copying the last step's first `nfields` fields into out[nfields, NY_local, NX] (ideally pinned memory)

@@ -185,11 +185,11 @@ int build_fft(plbm_ctx* c)
     if (dev_alloc(c, &f.T1, (size_t)nh * nyl)) return 1;
     if (R > 1) { if (dev_alloc(c, &f.T2, (size_t)(f.tab.nkl > 0 ? f.tab.nkl : 1) * n0)) return 1; }
     else f.T2 = f.T1;
-    f.row.n = n1; f.row.nstages = host_factorize(n1, f.row.radix); f.row.tw = c->tw_row;
-    f.col.n = n0; f.col.nstages = host_factorize(n0, f.col.radix); f.col.tw = c->tw_col;
+    f.row = make_fft_plan(n1, c->tw_row);
+    f.col = make_fft_plan(n0, c->tw_col);
     f.sx2 = c->sx2; f.sy2 = c->sy2;
     f.norm = 1.0 / (NX * NY);                              // reference src/poisson.cpp:415
-    CUDA_TRY(poisson_fft_configure());
+    CUDA_TRY(poisson_fft_configure(f));
     return 0;
 }
 

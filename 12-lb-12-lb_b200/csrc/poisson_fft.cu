@@ -18,43 +18,48 @@
 // Algorithmic traffic: P1 8+8, P2 8+8, P3 8+8, K3 8+16 = 72 B per cell.
 #include "poisson_fft.h"
 #include "fft.cuh"
+#include "host_tables.h"
 
 #include <type_traits>
-#include <utility>
+
 
 namespace plbm {
 
+// FFT_CAP = the largest CTA the instantiation may be launched with (sets the register budget:
+// 512 threads -> 128 registers, 768 -> 85 with spills; only sequences longer than 8192 need the latter).
+
+// two real rows as one complex sequence, read straight from global memory by the first pass
+struct RowPairIn {
+    const double* rowa; const double* rowb; bool paired;
+    static constexpr bool is_smem = false;
+    __device__ __forceinline__ cpx load(int j) const
+    {
+        cpx z;
+        z.re = __ldg(rowa + j);
+        z.im = paired ? __ldg(rowb + j) : 0.0;
+        return z;
+    }
+};
+
 // `in` holds the nyl local rows; T1 is [nh][nyl] (local rows), so the block of spectral columns a
 // peer owns is contiguous and can be sent as is.
-template <int THREADS, int EPT, bool TWS>
-__global__ void __launch_bounds__(THREADS)
+template <int FFT_CAP, int TAIL, bool ODD>
+__global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
                         int n0, int n1, int nh)
 {
     extern __shared__ cpx fbuf[];
-    const cpx* tw = plan.tw;
-    if (TWS) {                                     // twiddle table next to the sequence: no global latency inside the stages
-        cpx* tws = fbuf + plan.n;
-        for (int t = threadIdx.x; t < plan.n; t += blockDim.x) tws[t] = plan.tw[t];
-        tw = tws;
-    }
     const int ra = 2 * blockIdx.x, rb = ra + 1;        // local row pair; n0 = number of LOCAL rows here
     const bool paired = rb < n0;
-    const double* rowa = in + (size_t)ra * n1;
-    const double* rowb = in + (size_t)rb * n1;
-    for (int j = threadIdx.x; j < n1; j += blockDim.x) {
-        cpx z;
-        z.re = __ldg(rowa + j);
-        z.im = paired ? __ldg(rowb + j) : 0.0;
-        fbuf[j] = z;
-    }
-    fft_smem<-1, EPT, TWS>(fbuf, plan, tw);
+    const RowPairIn src{ in + (size_t)ra * n1, in + (size_t)rb * n1, paired };
+    const FftSmem sm{ fbuf };
+    fft_run<-1, TAIL, ODD>(plan, fbuf, src, sm);
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-        const cpx Z = fbuf[k];
+        const cpx Z = sm.load(k);
         if (!paired) {
             T[(size_t)k * n0 + ra] = Z;
         } else {
-            const cpx Zm = fbuf[k == 0 ? 0 : n1 - k];
+            const cpx Zm = sm.load(k == 0 ? 0 : n1 - k);
             cpx A, B;
             A.re = __dmul_rn(0.5, __dadd_rn(Z.re, Zm.re));
             A.im = __dmul_rn(0.5, __dsub_rn(Z.im, Zm.im));
@@ -66,80 +71,100 @@ poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, cons
     }
 }
 
-// One spectral column (all kx): forward, phi_hat = rho_hat / denom (poisson.cpp:388-409), inverse.
-// T2 holds this rank's columns as received from every rank s: [s][k_local][rows of s].
-template <int THREADS, int EPT, bool TWS>
-__global__ void __launch_bounds__(THREADS)
-poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
-                    const double* __restrict__ sx2, const double* __restrict__ sy2, int n0,
-                    const __grid_constant__ SlabTable tab, int k0)
-{
-    extern __shared__ cpx fbuf[];
-    const cpx* tw = plan.tw;
-    if (TWS) {                                     // twiddle table next to the sequence: no global latency inside the stages
-        cpx* tws = fbuf + plan.n;
-        for (int t = threadIdx.x; t < plan.n; t += blockDim.x) tws[t] = plan.tw[t];
-        tw = tws;
+// element i (row index of the whole lattice) of spectral column kl in T2 = [rank s][k_local][rows of s]
+struct ColumnIO {
+    cpx* T; const SlabTable* tab; int kl; int n0;
+    static constexpr bool is_smem = false;
+    __device__ __forceinline__ cpx* at(int i) const
+    {
+        if (tab->nranks == 1) return T + (size_t)kl * n0 + i;
+        int sr = 0;
+        while (i >= tab->y0[sr + 1]) ++sr;
+        const int rows = tab->y0[sr + 1] - tab->y0[sr];
+        return T + (size_t)tab->nkl * tab->y0[sr] + (size_t)kl * rows + (i - tab->y0[sr]);
     }
-    const int kl = blockIdx.x;
-    for (int sr = 0; sr < tab.nranks; ++sr) {
-        const int rows = tab.y0[sr + 1] - tab.y0[sr];
-        const cpx* seg = T + (size_t)tab.nkl * tab.y0[sr] + (size_t)kl * rows;
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) fbuf[tab.y0[sr] + r] = seg[r];
+    __device__ __forceinline__ cpx load(int i) const
+    {
+        const double2 t = *reinterpret_cast<const double2*>(at(i));
+        return { t.x, t.y };
     }
-    fft_smem<-1, EPT, TWS>(fbuf, plan, tw);
-    const double syk = __ldg(sy2 + k0 + kl);
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) {
+    __device__ __forceinline__ void store(int i, cpx v) const { *reinterpret_cast<double2*>(at(i)) = make_double2(v.re, v.im); }
+};
+
+// last pass of the forward column transform: phi_hat = rho_hat / denom (poisson.cpp:388-409), left in shared memory
+struct SymbolOut {
+    cpx* buf; const double* sx2; double syk;
+    static constexpr bool is_smem = true;
+    __device__ __forceinline__ void store(int i, cpx v) const
+    {
         const double denom = __dmul_rn(4.0, __dadd_rn(__ldg(sx2 + i), syk));
-        cpx v = fbuf[i];
         if (denom > 1e-15) {
             v.re = __ddiv_rn(v.re, denom);
             v.im = __ddiv_rn(v.im, denom);
         } else {
             v.re = 0.0; v.im = 0.0;
         }
-        fbuf[i] = v;
+        buf[fft_slot(i)] = v;
     }
-    fft_smem<+1, EPT, TWS>(fbuf, plan, tw);
-    for (int sr = 0; sr < tab.nranks; ++sr) {
-        const int rows = tab.y0[sr + 1] - tab.y0[sr];
-        cpx* seg = T + (size_t)tab.nkl * tab.y0[sr] + (size_t)kl * rows;
-        for (int r = threadIdx.x; r < rows; r += blockDim.x) seg[r] = fbuf[tab.y0[sr] + r];
-    }
+};
+
+// One spectral column (all kx): forward, division by the symbol, inverse -- the column never leaves the SM.
+template <int FFT_CAP, int TAIL, bool ODD>
+__global__ void __launch_bounds__(FFT_CAP, 1)
+poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
+                    const double* __restrict__ sx2, const double* __restrict__ sy2, int n0,
+                    const __grid_constant__ SlabTable tab, int k0)
+{
+    extern __shared__ cpx fbuf[];
+    const int kl = blockIdx.x;
+    const ColumnIO col{ T, &tab, kl, n0 };
+    const SymbolOut div{ fbuf, sx2, __ldg(sy2 + k0 + kl) };
+    const FftSmem sm{ fbuf };
+    fft_run<-1, TAIL, ODD>(plan, fbuf, col, div);
+    fft_run<+1, TAIL, ODD>(plan, fbuf, sm, col);
 }
 
-template <int THREADS, int EPT, bool TWS>
-__global__ void __launch_bounds__(THREADS)
+// packed spectrum of a row pair rebuilt on the fly from the two half spectra (c2r contract: the imaginary
+// parts of the DC and Nyquist terms are ignored)
+struct HalfSpectraIn {
+    const cpx* T; int n0, n1, ra; bool paired;
+    static constexpr bool is_smem = false;
+    __device__ __forceinline__ cpx load(int j) const
+    {
+        const bool lower = 2 * j <= n1;
+        const int k = lower ? j : n1 - j;
+        const double2* h = reinterpret_cast<const double2*>(T + (size_t)k * n0 + ra);
+        const double2 Ha = __ldg(h);
+        double2 Hb = make_double2(0.0, 0.0);
+        if (paired) Hb = __ldg(h + 1);
+        const bool self_conj = (k == 0) || (2 * k == n1);
+        const double ar = Ha.x, ai = self_conj ? 0.0 : Ha.y;
+        const double br = Hb.x, bi = self_conj ? 0.0 : Hb.y;
+        if (lower) return { __dsub_rn(ar, bi), __dadd_rn(ai, br) };
+        return { __dadd_rn(ar, bi), __dsub_rn(br, ai) };
+    }
+};
+struct RowPairOut {
+    double* rowa; double* rowb; bool paired; double norm;
+    static constexpr bool is_smem = false;
+    __device__ __forceinline__ void store(int j, cpx z) const
+    {
+        rowa[j] = __dmul_rn(z.re, norm);                        // poisson.cpp:415-419
+        if (paired) rowb[j] = __dmul_rn(z.im, norm);
+    }
+};
+
+template <int FFT_CAP, int TAIL, bool ODD>
+__global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, const __grid_constant__ FftPlan plan,
                         int n0, int n1, int nh, double norm)
 {
     extern __shared__ cpx fbuf[];
-    const cpx* tw = plan.tw;
-    if (TWS) {                                     // twiddle table next to the sequence: no global latency inside the stages
-        cpx* tws = fbuf + plan.n;
-        for (int t = threadIdx.x; t < plan.n; t += blockDim.x) tws[t] = plan.tw[t];
-        tw = tws;
-    }
     const int ra = 2 * blockIdx.x, rb = ra + 1;
     const bool paired = rb < n0;
-    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-        const cpx Ha = T[(size_t)k * n0 + ra];
-        cpx Hb = { 0.0, 0.0 };
-        if (paired) Hb = T[(size_t)k * n0 + rb];
-        const bool self_conj = (k == 0) || (2 * k == n1);      // DC / Nyquist: imaginary part ignored (c2r contract)
-        const double ar = Ha.re, ai = self_conj ? 0.0 : Ha.im;
-        const double br = Hb.re, bi = self_conj ? 0.0 : Hb.im;
-        fbuf[k] = { __dsub_rn(ar, bi), __dadd_rn(ai, br) };
-        if (!self_conj) fbuf[n1 - k] = { __dadd_rn(ar, bi), __dsub_rn(br, ai) };
-    }
-    fft_smem<+1, EPT, TWS>(fbuf, plan, tw);
-    double* rowa = phi + (size_t)ra * n1;
-    double* rowb = phi + (size_t)rb * n1;
-    for (int j = threadIdx.x; j < n1; j += blockDim.x) {
-        const cpx z = fbuf[j];
-        rowa[j] = __dmul_rn(z.re, norm);                        // poisson.cpp:415-419
-        if (paired) rowb[j] = __dmul_rn(z.im, norm);
-    }
+    const HalfSpectraIn src{ T, n0, n1, ra, paired };
+    const RowPairOut dst{ phi + (size_t)ra * n1, phi + (size_t)rb * n1, paired, norm };
+    fft_run<+1, TAIL, ODD>(plan, fbuf, src, dst);
 }
 
 // K3, poisson.cpp:589-607.  NY = local rows; below/above = the neighbouring slabs' boundary rows of
@@ -158,86 +183,99 @@ __global__ void efield_periodic_kernel(const double* __restrict__ phi, const dou
     Ey[row + i] = __dmul_rn(-0.5, __dsub_rn(__ldg(rp + i), __ldg(rm + i)));
 }
 
-// CTA shape per sequence length: THREADS threads, each holding at most EPT elements per stage
-// (THREADS * EPT >= n).  Small EPT keeps the butterflies in registers; 64 threads minimum.
-struct FftShape { int threads, ept; };
-static FftShape fft_shape(int n)
+FftPlan make_fft_plan(int n, const cpx* tw)
 {
-    if (n <= 64 * 4) return { 64, 4 };
-    if (n <= 128 * 4) return { 128, 4 };
-    if (n <= 256 * 4) return { 256, 4 };
-    if (n <= 256 * 8) return { 256, 8 };
-    if (n <= 512 * 8) return { 512, 8 };
-    if (n <= 1024 * 8) return { 1024, 8 };
-    return { 1024, 12 };
+    FftPlan P = {};
+    P.n = n; P.tw = tw;
+    int radix[64];
+    const int ns = host_factorize(n, radix);
+    int s = 1, nsub = n, log2s = 0;
+    for (int i = 0; i < ns;) {
+        FftPass& ps = P.pass[P.npass++];
+        ps.s = s; ps.log2s = log2s;
+        int R;
+        if (radix[i] == 4 && i + 1 < ns && radix[i + 1] == 4) { ps.kind = FFT_PASS_44; R = 16; i += 2; P.n44++; }
+        else if (radix[i] == 4 && i + 1 < ns && radix[i + 1] == 2) { ps.kind = FFT_PASS_42; R = 8; i += 2; P.tail = FFT_TAIL_42; }
+        else if (radix[i] == 4) { ps.kind = FFT_PASS_4; R = 4; i += 1; P.tail = FFT_TAIL_4; }
+        else if (radix[i] == 2) { ps.kind = FFT_PASS_2; R = 2; i += 1; P.tail = FFT_TAIL_2; }
+        else { ps.kind = FFT_PASS_ODD; R = radix[i]; ps.r = (unsigned short)R; i += 1; P.has_odd = 1; }
+        nsub /= R;
+        ps.m = nsub;
+        s *= R;
+        while ((1 << (log2s + 1)) <= s) ++log2s;
+    }
+    return P;
 }
 
+static size_t fft_smem_bytes(int n) { return sizeof(cpx) * (size_t)fft_smem_elems(n); }
+
+// kernels are specialised on the plan's shape (tail pass kind, odd passes present) and on the CTA cap
 template <class F>
-static cudaError_t with_shape(int n, F&& f)
+static cudaError_t with_shape(const FftPlan& P, int threads, F&& f)
 {
-    const FftShape s = fft_shape(n);
-    if (s.threads == 64) return f(std::integral_constant<int, 64>{}, std::integral_constant<int, 4>{});
-    if (s.threads == 128) return f(std::integral_constant<int, 128>{}, std::integral_constant<int, 4>{});
-    if (s.threads == 256 && s.ept == 4) return f(std::integral_constant<int, 256>{}, std::integral_constant<int, 4>{});
-    if (s.threads == 256) return f(std::integral_constant<int, 256>{}, std::integral_constant<int, 8>{});
-    if (s.threads == 512) return f(std::integral_constant<int, 512>{}, std::integral_constant<int, 8>{});
-    if (s.ept == 8) return f(std::integral_constant<int, 1024>{}, std::integral_constant<int, 8>{});
-    return f(std::integral_constant<int, 1024>{}, std::integral_constant<int, 12>{});
+    auto cap = [&](auto TAIL, auto ODD) {
+        if (threads <= 512) return f(std::integral_constant<int, 512>{}, TAIL, ODD);
+        return f(std::integral_constant<int, 768>{}, TAIL, ODD);
+    };
+    auto odd = [&](auto TAIL) {
+        if (P.has_odd) return cap(TAIL, std::true_type{});
+        return cap(TAIL, std::false_type{});
+    };
+    switch (P.tail) {
+    case FFT_TAIL_42: return odd(std::integral_constant<int, FFT_TAIL_42>{});
+    case FFT_TAIL_4: return odd(std::integral_constant<int, FFT_TAIL_4>{});
+    case FFT_TAIL_2: return odd(std::integral_constant<int, FFT_TAIL_2>{});
+    default: return odd(std::integral_constant<int, FFT_TAIL_NONE>{});
+    }
 }
-
-// up to this length the twiddle table travels with the sequence in shared memory (2 x 16 B x n <= 128 KB)
-static bool tw_in_smem(int n) { (void)n; return false; }   // measured: no gain on B200 (the stages are bound by shared-memory round trips, not twiddle latency)
 
 template <class K>
 static cudaError_t allow_smem(K kernel)
 {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(cpx) * FFT_MAX_N));
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem_bytes(FFT_MAX_N));
 }
 
-cudaError_t poisson_fft_configure()
+cudaError_t poisson_fft_configure(const PoissonFftDev& p)
 {
-    cudaError_t e = cudaSuccess;
-    auto all = [&](auto T, auto E) {
-        constexpr int t = decltype(T)::value, p = decltype(E)::value;
-        if (e == cudaSuccess) e = allow_smem(poisson_rows_fwd_kernel<t, p, false>);
-        if (e == cudaSuccess) e = allow_smem(poisson_cols_kernel<t, p, false>);
-        if (e == cudaSuccess) e = allow_smem(poisson_rows_inv_kernel<t, p, false>);
-        if (e == cudaSuccess) e = allow_smem(poisson_rows_fwd_kernel<t, p, true>);
-        if (e == cudaSuccess) e = allow_smem(poisson_cols_kernel<t, p, true>);
-        if (e == cudaSuccess) e = allow_smem(poisson_rows_inv_kernel<t, p, true>);
-        return e;
-    };
-    for (int n : { 256, 512, 1024, 2048, 4096, 8192, 12288 }) with_shape(n, all);
-    return e;
+    cudaError_t e = with_shape(p.row, fft_threads(p.n1), [&](auto CAP, auto TAIL, auto ODD) {
+        cudaError_t r = allow_smem(poisson_rows_fwd_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
+        if (r == cudaSuccess) r = allow_smem(poisson_rows_inv_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
+        return r;
+    });
+    if (e != cudaSuccess) return e;
+    return with_shape(p.col, fft_threads(p.n0), [&](auto CAP, auto TAIL, auto ODD) {
+        return allow_smem(poisson_cols_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
+    });
 }
 
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream)
 {
-    const int nh = p.n1 / 2 + 1;
-    return with_shape(p.n1, [&](auto T, auto E) {
-        constexpr int t = decltype(T)::value, e = decltype(E)::value;
-        if (tw_in_smem(p.n1)) poisson_rows_fwd_kernel<t, e, true><<<(p.nyl + 1) / 2, t, 2 * sizeof(cpx) * p.n1, stream>>>(rho_q, p.T1, p.row, p.nyl, p.n1, nh);
-        else poisson_rows_fwd_kernel<t, e, false><<<(p.nyl + 1) / 2, t, sizeof(cpx) * p.n1, stream>>>(rho_q, p.T1, p.row, p.nyl, p.n1, nh);
+    const int nh = p.n1 / 2 + 1, t = fft_threads(p.n1), grid = (p.nyl + 1) / 2;
+    const size_t sm = fft_smem_bytes(p.n1);
+    return with_shape(p.row, t, [&](auto CAP, auto TAIL, auto ODD) {
+        poisson_rows_fwd_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
+            <<<grid, t, sm, stream>>>(rho_q, p.T1, p.row, p.nyl, p.n1, nh);
         return cudaGetLastError();
     });
 }
 cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream)
 {
     if (p.tab.nkl <= 0) return cudaSuccess;
-    return with_shape(p.n0, [&](auto T, auto E) {
-        constexpr int t = decltype(T)::value, e = decltype(E)::value;
-        if (tw_in_smem(p.n0)) poisson_cols_kernel<t, e, true><<<p.tab.nkl, t, 2 * sizeof(cpx) * p.n0, stream>>>(p.T2, p.col, p.sx2, p.sy2, p.n0, p.tab, p.k0);
-        else poisson_cols_kernel<t, e, false><<<p.tab.nkl, t, sizeof(cpx) * p.n0, stream>>>(p.T2, p.col, p.sx2, p.sy2, p.n0, p.tab, p.k0);
+    const int t = fft_threads(p.n0);
+    const size_t sm = fft_smem_bytes(p.n0);
+    return with_shape(p.col, t, [&](auto CAP, auto TAIL, auto ODD) {
+        poisson_cols_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
+            <<<p.tab.nkl, t, sm, stream>>>(p.T2, p.col, p.sx2, p.sy2, p.n0, p.tab, p.k0);
         return cudaGetLastError();
     });
 }
 cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream)
 {
-    const int nh = p.n1 / 2 + 1;
-    return with_shape(p.n1, [&](auto T, auto E) {
-        constexpr int t = decltype(T)::value, e = decltype(E)::value;
-        if (tw_in_smem(p.n1)) poisson_rows_inv_kernel<t, e, true><<<(p.nyl + 1) / 2, t, 2 * sizeof(cpx) * p.n1, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
-        else poisson_rows_inv_kernel<t, e, false><<<(p.nyl + 1) / 2, t, sizeof(cpx) * p.n1, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
+    const int nh = p.n1 / 2 + 1, t = fft_threads(p.n1), grid = (p.nyl + 1) / 2;
+    const size_t sm = fft_smem_bytes(p.n1);
+    return with_shape(p.row, t, [&](auto CAP, auto TAIL, auto ODD) {
+        poisson_rows_inv_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
+            <<<grid, t, sm, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
         return cudaGetLastError();
     });
 }

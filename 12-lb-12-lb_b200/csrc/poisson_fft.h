@@ -27,7 +27,8 @@ struct PoissonFftDev {
     double norm;         // 1.0 / (NX*NY)                           (poisson.cpp:415)
 };
 
-cudaError_t poisson_fft_configure();
+FftPlan make_fft_plan(int n, const cpx* tw);   // pass schedule for length n (radix schedule of oracle/fft_oracle.c, grouped)
+cudaError_t poisson_fft_configure(const PoissonFftDev& p);   // after row/col plans are set
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream);   // rho_q -> T1
 cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream);                            // T2 in place
 cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream);           // T1 -> phi
