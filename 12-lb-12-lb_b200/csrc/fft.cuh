@@ -26,7 +26,7 @@
 
 namespace plbm {
 
-struct cpx {
+struct __align__(16) cpx {
     double re, im;
 };
 

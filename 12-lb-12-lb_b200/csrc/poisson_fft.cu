@@ -28,6 +28,16 @@ namespace plbm {
 // FFT_CAP = the largest CTA the instantiation may be launched with (sets the register budget:
 // 512 threads -> 128 registers, 768 -> 85 with spills; only sequences longer than 8192 need the latter).
 
+// (A, B) of a row pair are neighbours in T[k][row]: one 256-bit access when the pair is 32-byte aligned
+__device__ __forceinline__ void store_pair(cpx* p, cpx a, cpx b)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a.re), "d"(a.im), "d"(b.re), "d"(b.im) : "memory");
+}
+__device__ __forceinline__ void load_pair(const cpx* p, cpx& a, cpx& b)
+{
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.re), "=d"(a.im), "=d"(b.re), "=d"(b.im) : "l"(p));
+}
+
 // two real rows as one complex sequence, read straight from global memory by the first pass
 struct RowPairIn {
     const double* rowa; const double* rowb; bool paired;
@@ -54,20 +64,23 @@ poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, cons
     const RowPairIn src{ in + (size_t)ra * n1, in + (size_t)rb * n1, paired };
     const FftSmem sm{ fbuf };
     fft_run<-1, TAIL, ODD>(plan, fbuf, src, sm);
+    if (!paired) {
+        for (int k = threadIdx.x; k < nh; k += blockDim.x) T[(size_t)k * n0 + ra] = sm.load(k);
+        return;
+    }
+    const bool wide = (n0 & 1) == 0;                   // (k*n0 + ra) even: the pair is 32-byte aligned
+    #pragma unroll 4
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
         const cpx Z = sm.load(k);
-        if (!paired) {
-            T[(size_t)k * n0 + ra] = Z;
-        } else {
-            const cpx Zm = sm.load(k == 0 ? 0 : n1 - k);
-            cpx A, B;
-            A.re = __dmul_rn(0.5, __dadd_rn(Z.re, Zm.re));
-            A.im = __dmul_rn(0.5, __dsub_rn(Z.im, Zm.im));
-            B.re = __dmul_rn(0.5, __dadd_rn(Z.im, Zm.im));
-            B.im = __dmul_rn(0.5, __dsub_rn(Zm.re, Z.re));
-            T[(size_t)k * n0 + ra] = A;
-            T[(size_t)k * n0 + rb] = B;
-        }
+        const cpx Zm = sm.load(k == 0 ? 0 : n1 - k);
+        cpx A, B;
+        A.re = __dmul_rn(0.5, __dadd_rn(Z.re, Zm.re));
+        A.im = __dmul_rn(0.5, __dsub_rn(Z.im, Zm.im));
+        B.re = __dmul_rn(0.5, __dadd_rn(Z.im, Zm.im));
+        B.im = __dmul_rn(0.5, __dsub_rn(Zm.re, Z.re));
+        cpx* dst = T + (size_t)k * n0 + ra;
+        if (wide) store_pair(dst, A, B);
+        else { dst[0] = A; dst[1] = B; }
     }
 }
 
@@ -124,26 +137,6 @@ poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
     fft_run<+1, TAIL, ODD>(plan, fbuf, sm, col);
 }
 
-// packed spectrum of a row pair rebuilt on the fly from the two half spectra (c2r contract: the imaginary
-// parts of the DC and Nyquist terms are ignored)
-struct HalfSpectraIn {
-    const cpx* T; int n0, n1, ra; bool paired;
-    static constexpr bool is_smem = false;
-    __device__ __forceinline__ cpx load(int j) const
-    {
-        const bool lower = 2 * j <= n1;
-        const int k = lower ? j : n1 - j;
-        const double2* h = reinterpret_cast<const double2*>(T + (size_t)k * n0 + ra);
-        const double2 Ha = __ldg(h);
-        double2 Hb = make_double2(0.0, 0.0);
-        if (paired) Hb = __ldg(h + 1);
-        const bool self_conj = (k == 0) || (2 * k == n1);
-        const double ar = Ha.x, ai = self_conj ? 0.0 : Ha.y;
-        const double br = Hb.x, bi = self_conj ? 0.0 : Hb.y;
-        if (lower) return { __dsub_rn(ar, bi), __dadd_rn(ai, br) };
-        return { __dadd_rn(ar, bi), __dsub_rn(br, ai) };
-    }
-};
 struct RowPairOut {
     double* rowa; double* rowb; bool paired; double norm;
     static constexpr bool is_smem = false;
@@ -162,9 +155,25 @@ poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, con
     extern __shared__ cpx fbuf[];
     const int ra = 2 * blockIdx.x, rb = ra + 1;
     const bool paired = rb < n0;
-    const HalfSpectraIn src{ T, n0, n1, ra, paired };
+    // packed spectrum of the row pair rebuilt from the two half spectra (c2r contract: the imaginary parts of the
+    // DC and Nyquist terms are ignored); every (Ha, Hb) is fetched once and feeds elements k and n1-k
+    const FftSmem sm{ fbuf };
+    const bool wide = paired && (n0 & 1) == 0;
+    #pragma unroll 4
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        const cpx* h = T + (size_t)k * n0 + ra;
+        cpx Ha, Hb = { 0.0, 0.0 };
+        if (wide) load_pair(h, Ha, Hb);
+        else { Ha = h[0]; if (paired) Hb = h[1]; }
+        const bool self_conj = (k == 0) || (2 * k == n1);
+        const double ar = Ha.re, ai = self_conj ? 0.0 : Ha.im;
+        const double br = Hb.re, bi = self_conj ? 0.0 : Hb.im;
+        sm.store(k, { __dsub_rn(ar, bi), __dadd_rn(ai, br) });
+        if (!self_conj) sm.store(n1 - k, { __dadd_rn(ar, bi), __dsub_rn(br, ai) });
+    }
+    __syncthreads();
     const RowPairOut dst{ phi + (size_t)ra * n1, phi + (size_t)rb * n1, paired, norm };
-    fft_run<+1, TAIL, ODD>(plan, fbuf, src, dst);
+    fft_run<+1, TAIL, ODD>(plan, fbuf, sm, dst);
 }
 
 // K3, poisson.cpp:589-607.  NY = local rows; below/above = the neighbouring slabs' boundary rows of
