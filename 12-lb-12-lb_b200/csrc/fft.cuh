@@ -49,19 +49,14 @@ struct FftPlan {
     int npass;
     int n44;                        // leading FFT_PASS_44 passes
     int tail;                       // FftTail: the 4/2 pass after them
-    int has_odd;
+    int odd;                        // FftOdd
+    int threads;                    // CTA size the passes need: ceil(n/16), or ceil(n/15) with radix-3/5 register passes
     FftPass pass[FFT_MAX_PASSES];
     const cpx* tw;                  // device: n forward twiddles exp(-2 pi i t / n)
 };
 
 __host__ __device__ __forceinline__ int fft_slot(int i) { return i + (i >> 4); }
 __host__ __device__ __forceinline__ int fft_smem_elems(int n) { return fft_slot(n > 0 ? n - 1 : 0) + 1; }
-__host__ __device__ __forceinline__ int fft_threads(int n)
-{
-    const int t = ((n + FFT_EPT - 1) / FFT_EPT + 31) & ~31;
-    return t < 64 ? 64 : t;
-}
-
 __device__ __forceinline__ cpx cadd(cpx a, cpx b) { return { __dadd_rn(a.re, b.re), __dadd_rn(a.im, b.im) }; }
 __device__ __forceinline__ cpx csub(cpx a, cpx b) { return { __dsub_rn(a.re, b.re), __dsub_rn(a.im, b.im) }; }
 __device__ __forceinline__ cpx cmul(cpx a, cpx w)
@@ -224,16 +219,63 @@ __device__ __forceinline__ void fft_pass_odd(int n, const FftPass ps, const cpx*
     if (out.is_smem()) __syncthreads();
 }
 
+// radix 3 or 5 on registers: a thread forms whole butterflies (all R outputs from R inputs), 16/R of them,
+// with exactly the generic pass's arithmetic per output (terms in k order, w_R^e taken from the table).
+template <int SIGN, int R, class In, class Out>
+__device__ __forceinline__ void fft_pass_small_odd(int n, const FftPass ps, const cpx* __restrict__ tw, const In& in, const Out& out)
+{
+    constexpr int BPT = FFT_EPT / R;
+    const int nb = n / R, nt = blockDim.x, s = ps.s;
+    cpx w[R];                                                     // w[e] = w_R^e = W[e * n / R]
+    #pragma unroll
+    for (int e = 1; e < R; ++e) w[e] = twiddle<SIGN>(tw, e * nb);
+    cpx v[BPT][R];
+    #pragma unroll
+    for (int e = 0; e < BPT; ++e) {
+        const int b = threadIdx.x + e * nt;                       // b = q + s*p
+        if (b < nb) {
+            cpx a[R];
+            #pragma unroll
+            for (int k = 0; k < R; ++k) a[k] = in.load(b + nb * k);   // s*m == nb
+            const int ps_ = (b / s) * s;                          // p * s
+            #pragma unroll
+            for (int j = 0; j < R; ++j) {
+                cpx acc = a[0];
+                #pragma unroll
+                for (int k = 1; k < R; ++k) {
+                    if (j == 0) acc = cadd(acc, a[k]);
+                    else acc = cadd(acc, cmul(a[k], w[(j * k) % R]));
+                }
+                if (j != 0 && ps_ != 0) acc = cmul(acc, twiddle<SIGN>(tw, j * ps_));
+                v[e][j] = acc;
+            }
+        }
+    }
+    if (in.is_smem() && out.is_smem()) __syncthreads();
+    #pragma unroll
+    for (int e = 0; e < BPT; ++e) {
+        const int b = threadIdx.x + e * nt;
+        if (b < nb) {
+            const int p = b / s, q = b - p * s;
+            #pragma unroll
+            for (int j = 0; j < R; ++j) out.store(q + s * (R * p + j), v[e][j]);
+        }
+    }
+    if (out.is_smem()) __syncthreads();
+}
+
 // Shape of a plan that the kernels are specialised on: the schedule is always [4,4]* then at most one of
 // (4,2) / (4) / (2), then odd primes.  Keeping the pass bodies out of a runtime switch lets ptxas allocate each
 // body's 16 complex registers independently (a switch over the bodies made it spill).
 enum FftTail { FFT_TAIL_NONE = 0, FFT_TAIL_42 = 1, FFT_TAIL_4 = 2, FFT_TAIL_2 = 3 };
+// odd part of the schedule: none; 3 / 5 = every odd stage has that radix (register passes); generic otherwise
+enum FftOdd { FFT_ODD_NONE = 0, FFT_ODD_GENERIC = 1, FFT_ODD_3 = 3, FFT_ODD_5 = 5 };
 
 // Transform of length P.n from `in` to `out` (element index -> value functors with load/store and a static
 // `is_smem`), through the padded shared buffer `buf`.  All threads of the CTA must call it.  If `in` reads shared
 // memory, its contents must be visible (barrier) before the call; if `out` writes shared memory, the result is
-// visible to every thread on return.  TAIL / ODD must describe P (fft_plan_tail, fft_plan_has_odd).
-template <int SIGN, int TAIL, bool ODD, class In, class Out>
+// visible to every thread on return.  TAIL / ODD must describe P (P.tail, P.odd).
+template <int SIGN, int TAIL, int ODD, class In, class Out>
 __device__ __forceinline__ void fft_run(const FftPlan& P, cpx* buf, const In& in, const Out& out)
 {
     if (P.npass == 0) {                                           // n == 1
@@ -257,12 +299,13 @@ __device__ __forceinline__ void fft_run(const FftPlan& P, cpx* buf, const In& in
         else fft_pass_pow2<SIGN, 2, 1>(P.n, P.pass[i], P.tw, src, dst);
         ++i;
     }
-    if constexpr (ODD) {
+    if constexpr (ODD != FFT_ODD_NONE) {
         #pragma unroll 1
         for (; i < P.npass; ++i) {
             const FftSource<In> src{ in, buf, i == 0 };
             const FftSink<Out> dst{ out, buf, i == last };
-            fft_pass_odd<SIGN>(P.n, P.pass[i], P.tw, src, dst);
+            if constexpr (ODD == 3 || ODD == 5) fft_pass_small_odd<SIGN, ODD>(P.n, P.pass[i], P.tw, src, dst);
+            else fft_pass_odd<SIGN>(P.n, P.pass[i], P.tw, src, dst);
         }
     }
 }

@@ -53,7 +53,7 @@ struct RowPairIn {
 
 // `in` holds the nyl local rows; T1 is [nh][nyl] (local rows), so the block of spectral columns a
 // peer owns is contiguous and can be sent as is.
-template <int FFT_CAP, int TAIL, bool ODD>
+template <int FFT_CAP, int TAIL, int ODD>
 __global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_rows_fwd_kernel(const double* __restrict__ in, cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
                         int n0, int n1, int nh)
@@ -122,7 +122,7 @@ struct SymbolOut {
 };
 
 // One spectral column (all kx): forward, division by the symbol, inverse -- the column never leaves the SM.
-template <int FFT_CAP, int TAIL, bool ODD>
+template <int FFT_CAP, int TAIL, int ODD>
 __global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_cols_kernel(cpx* __restrict__ T, const __grid_constant__ FftPlan plan,
                     const double* __restrict__ sx2, const double* __restrict__ sy2, int n0,
@@ -147,7 +147,7 @@ struct RowPairOut {
     }
 };
 
-template <int FFT_CAP, int TAIL, bool ODD>
+template <int FFT_CAP, int TAIL, int ODD>
 __global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, const __grid_constant__ FftPlan plan,
                         int n0, int n1, int nh, double norm)
@@ -207,11 +207,22 @@ FftPlan make_fft_plan(int n, const cpx* tw)
         else if (radix[i] == 4 && i + 1 < ns && radix[i + 1] == 2) { ps.kind = FFT_PASS_42; R = 8; i += 2; P.tail = FFT_TAIL_42; }
         else if (radix[i] == 4) { ps.kind = FFT_PASS_4; R = 4; i += 1; P.tail = FFT_TAIL_4; }
         else if (radix[i] == 2) { ps.kind = FFT_PASS_2; R = 2; i += 1; P.tail = FFT_TAIL_2; }
-        else { ps.kind = FFT_PASS_ODD; R = radix[i]; ps.r = (unsigned short)R; i += 1; P.has_odd = 1; }
+        else {
+            ps.kind = FFT_PASS_ODD; R = radix[i]; ps.r = (unsigned short)R; i += 1;
+            const int small = (R == 3 || R == 5) ? R : FFT_ODD_GENERIC;
+            P.odd = (P.odd == FFT_ODD_NONE || P.odd == small) ? small : FFT_ODD_GENERIC;
+        }
         nsub /= R;
         ps.m = nsub;
         s *= R;
         while ((1 << (log2s + 1)) <= s) ++log2s;
+    }
+    const int per_thread = (P.odd == FFT_ODD_3 || P.odd == FFT_ODD_5) ? 15 : FFT_EPT;
+    P.threads = ((n + per_thread - 1) / per_thread + 31) & ~31;
+    if (P.threads < 64) P.threads = 64;
+    if (P.threads > 512 && P.odd != FFT_ODD_NONE) {               // the 768-thread kernels carry the generic odd pass only
+        P.odd = FFT_ODD_GENERIC;
+        P.threads = ((n + FFT_EPT - 1) / FFT_EPT + 31) & ~31;
     }
     return P;
 }
@@ -220,15 +231,19 @@ static size_t fft_smem_bytes(int n) { return sizeof(cpx) * (size_t)fft_smem_elem
 
 // kernels are specialised on the plan's shape (tail pass kind, odd passes present) and on the CTA cap
 template <class F>
-static cudaError_t with_shape(const FftPlan& P, int threads, F&& f)
+static cudaError_t with_shape(const FftPlan& P, F&& f)
 {
-    auto cap = [&](auto TAIL, auto ODD) {
-        if (threads <= 512) return f(std::integral_constant<int, 512>{}, TAIL, ODD);
-        return f(std::integral_constant<int, 768>{}, TAIL, ODD);
-    };
     auto odd = [&](auto TAIL) {
-        if (P.has_odd) return cap(TAIL, std::true_type{});
-        return cap(TAIL, std::false_type{});
+        if (P.threads > 512) {
+            if (P.odd != FFT_ODD_NONE) return f(std::integral_constant<int, 768>{}, TAIL, std::integral_constant<int, FFT_ODD_GENERIC>{});
+            return f(std::integral_constant<int, 768>{}, TAIL, std::integral_constant<int, FFT_ODD_NONE>{});
+        }
+        switch (P.odd) {
+        case FFT_ODD_3: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_3>{});
+        case FFT_ODD_5: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_5>{});
+        case FFT_ODD_GENERIC: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_GENERIC>{});
+        default: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_NONE>{});
+        }
     };
     switch (P.tail) {
     case FFT_TAIL_42: return odd(std::integral_constant<int, FFT_TAIL_42>{});
@@ -246,22 +261,22 @@ static cudaError_t allow_smem(K kernel)
 
 cudaError_t poisson_fft_configure(const PoissonFftDev& p)
 {
-    cudaError_t e = with_shape(p.row, fft_threads(p.n1), [&](auto CAP, auto TAIL, auto ODD) {
+    cudaError_t e = with_shape(p.row, [&](auto CAP, auto TAIL, auto ODD) {
         cudaError_t r = allow_smem(poisson_rows_fwd_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
         if (r == cudaSuccess) r = allow_smem(poisson_rows_inv_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
         return r;
     });
     if (e != cudaSuccess) return e;
-    return with_shape(p.col, fft_threads(p.n0), [&](auto CAP, auto TAIL, auto ODD) {
+    return with_shape(p.col, [&](auto CAP, auto TAIL, auto ODD) {
         return allow_smem(poisson_cols_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>);
     });
 }
 
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream)
 {
-    const int nh = p.n1 / 2 + 1, t = fft_threads(p.n1), grid = (p.nyl + 1) / 2;
+    const int nh = p.n1 / 2 + 1, t = p.row.threads, grid = (p.nyl + 1) / 2;
     const size_t sm = fft_smem_bytes(p.n1);
-    return with_shape(p.row, t, [&](auto CAP, auto TAIL, auto ODD) {
+    return with_shape(p.row, [&](auto CAP, auto TAIL, auto ODD) {
         poisson_rows_fwd_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
             <<<grid, t, sm, stream>>>(rho_q, p.T1, p.row, p.nyl, p.n1, nh);
         return cudaGetLastError();
@@ -270,9 +285,9 @@ cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q,
 cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream)
 {
     if (p.tab.nkl <= 0) return cudaSuccess;
-    const int t = fft_threads(p.n0);
+    const int t = p.col.threads;
     const size_t sm = fft_smem_bytes(p.n0);
-    return with_shape(p.col, t, [&](auto CAP, auto TAIL, auto ODD) {
+    return with_shape(p.col, [&](auto CAP, auto TAIL, auto ODD) {
         poisson_cols_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
             <<<p.tab.nkl, t, sm, stream>>>(p.T2, p.col, p.sx2, p.sy2, p.n0, p.tab, p.k0);
         return cudaGetLastError();
@@ -280,9 +295,9 @@ cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream)
 }
 cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream)
 {
-    const int nh = p.n1 / 2 + 1, t = fft_threads(p.n1), grid = (p.nyl + 1) / 2;
+    const int nh = p.n1 / 2 + 1, t = p.row.threads, grid = (p.nyl + 1) / 2;
     const size_t sm = fft_smem_bytes(p.n1);
-    return with_shape(p.row, t, [&](auto CAP, auto TAIL, auto ODD) {
+    return with_shape(p.row, [&](auto CAP, auto TAIL, auto ODD) {
         poisson_rows_inv_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
             <<<grid, t, sm, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
         return cudaGetLastError();
