@@ -51,6 +51,54 @@ __global__ void recip_kernel(const double* d, double* y, int n)
     if (t < n) y[t] = recip_refined(d[t]);
 }
 
+// Barrier among the slabs' streams: every rank publishes the epoch in its slot of every peer's flag array and waits
+// until all slots of its own array have reached it.  Work enqueued before the barrier on any rank (its peer-memory
+// writes included: release at system scope after the preceding kernels completed) is visible to work enqueued after
+// it on every rank.  One GPU per rank, so the spinning CTA never keeps a peer's kernels from running.
+struct PeerFlags {
+    unsigned long long* f[PLBM_MAX_RANKS];
+};
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags pf, int rank, int nranks, unsigned long long epoch, int* timeout)
+{
+    const int t = threadIdx.x;
+    if (t < nranks) {
+        __threadfence_system();
+        unsigned long long* theirs = pf.f[t] + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(theirs), "l"(epoch) : "memory");
+        const unsigned long long* mine = pf.f[rank] + t;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 20000000000ll) { *timeout = 1; break; }     // ~10 s: a peer died; do not hang the GPU
+        }
+        __threadfence_system();
+    }
+}
+
+struct PeerBlob {                       // what one rank tells the others (plbm_peer_export)
+    cudaIpcMemHandle_t t1, flags;
+    long long t1_offset, flags_offset;  // of the pointer inside the IPC-mapped allocation
+    int rank, nyl;
+};
+static_assert(sizeof(PeerBlob) <= PLBM_PEER_BLOB_BYTES, "PLBM_PEER_BLOB_BYTES too small");
+
+// offset of p inside the allocation an IPC handle of p maps (cudaMalloc may sub-allocate)
+int allocation_offset(const void* p, long long* off)
+{
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &st));
+    if (!fn || st != cudaDriverEntryPointSuccess) return fail("cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (((range_fn)fn)(&base, &size, (unsigned long long)p) != 0) return fail("cuMemGetAddressRange failed");
+    *off = (long long)((unsigned long long)p - base);
+    return 0;
+}
+
 } // namespace
 
 int plbm_set_error(const char* msg) { return fail("%s", msg); }
@@ -79,6 +127,14 @@ struct plbm_ctx {
     // multi-slab exchange buffers
     double* halo_send_lo = nullptr; double* halo_send_hi = nullptr; double* halo_recv_lo = nullptr; double* halo_recv_hi = nullptr;
     double* phi_below = nullptr; double* phi_above = nullptr;
+    // peer-memory transposes: every slab's T1 and barrier flags mapped through CUDA IPC
+    bool peers = false;
+    PeerTable peer_t1 = {};
+    unsigned long long* flags = nullptr;                 // [PLBM_MAX_RANKS] arrival counters written by the peers
+    unsigned long long* peer_flags[PLBM_MAX_RANKS] = {};
+    void* peer_mapped[2 * PLBM_MAX_RANKS] = {};          // bases returned by cudaIpcOpenMemHandle
+    int* peer_timeout = nullptr;                         // device flag: a barrier gave up waiting
+    unsigned long long epoch = 0;
     int slab_y0[PLBM_MAX_RANKS + 1] = {};
     int slab_k0[PLBM_MAX_RANKS + 1] = {};
     // unfused device path (bounce-back walls): the reference's own array set in its own layout
@@ -428,6 +484,8 @@ void plbm_destroy(plbm_ctx* c)
     for (auto e : c->events) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) cudaFree(c->pop[b]);
     cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
+    for (void* m : c->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(c->flags); cudaFree(c->peer_timeout);
     for (int b = 0; b < 2; ++b) for (int k = 0; k < 12; ++k) cudaFree(c->macro_sets[b][k]);
     for (int k = 0; k < 4; ++k) cudaFree(c->snap[k]);
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
@@ -751,8 +809,97 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
     case 1: CUDA_TRY(launch_poisson_cols(c->fft, c->stream)); return 0;
     case 2: CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream)); return 0;
     case 3: return poisson_efield(c, PLBM_BC_PERIODIC, nullptr);
+    case 4:
+        if (!c->peers) return fail("plbm_poisson_stage(4): peer memory is not attached (plbm_peer_attach)");
+        CUDA_TRY(launch_poisson_cols(c->fft, c->stream, &c->peer_t1));
+        return 0;
     default: return fail("plbm_poisson_stage: stage %d", stage);
     }
+}
+
+int plbm_peer_export(plbm_ctx* c, void* blob)
+{
+    if (!c || !blob) return fail("plbm_peer_export: null argument");
+    if (c->cfg.nranks < 2 || !c->fft.T1) return fail("plbm_peer_export: needs a multi-slab context with the spectral Poisson solve");
+    if (!c->flags) {
+        if (dev_alloc(c, &c->flags, PLBM_MAX_RANKS)) return 1;
+        if (dev_alloc(c, &c->peer_timeout, 1)) return 1;
+        CUDA_TRY(cudaMemset(c->flags, 0, sizeof(unsigned long long) * PLBM_MAX_RANKS));
+        CUDA_TRY(cudaMemset(c->peer_timeout, 0, sizeof(int)));
+    }
+    PeerBlob b;
+    std::memset(&b, 0, sizeof(b));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.t1, c->fft.T1));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->flags));
+    if (allocation_offset(c->fft.T1, &b.t1_offset) || allocation_offset(c->flags, &b.flags_offset)) return 1;
+    b.rank = c->cfg.rank; b.nyl = c->geom.NYl;
+    std::memset(blob, 0, PLBM_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+int plbm_peer_attach(plbm_ctx* c, const void* blobs)
+{
+    if (!c || !blobs) return fail("plbm_peer_attach: null argument");
+    if (!c->flags) return fail("plbm_peer_attach: call plbm_peer_export first");
+    if (c->peers) return 0;
+    const int R = c->cfg.nranks;
+    for (int s = 0; s < R; ++s) {
+        PeerBlob b;
+        std::memcpy(&b, (const char*)blobs + (size_t)s * PLBM_PEER_BLOB_BYTES, sizeof(b));
+        if (b.rank != s || b.nyl != c->slab_y0[s + 1] - c->slab_y0[s]) return fail("plbm_peer_attach: blob %d does not describe slab %d", s, s);
+        if (s == c->cfg.rank) {
+            c->peer_t1.t1[s] = c->fft.T1;
+            c->peer_flags[s] = c->flags;
+            continue;
+        }
+        void *t1 = nullptr, *fl = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&t1, b.t1, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_mapped[2 * s] = t1;
+        // T1 and the flags may live in the same underlying allocation: a second open of the same handle fails
+        if (std::memcmp(&b.t1, &b.flags, sizeof(cudaIpcMemHandle_t)) == 0) fl = t1;
+        else {
+            CUDA_TRY(cudaIpcOpenMemHandle(&fl, b.flags, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_mapped[2 * s + 1] = fl;
+        }
+        c->peer_t1.t1[s] = (cpx*)((char*)t1 + b.t1_offset);
+        c->peer_flags[s] = (unsigned long long*)((char*)fl + b.flags_offset);
+    }
+    c->peers = true;
+    return 0;
+}
+
+int plbm_peer_detach(plbm_ctx* c)
+{
+    if (!c) return fail("plbm_peer_detach: null context");
+    if (c->stream) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (void*& m : c->peer_mapped) {
+        if (m) CUDA_TRY(cudaIpcCloseMemHandle(m));
+        m = nullptr;
+    }
+    c->peers = false;
+    return 0;
+}
+
+int plbm_peer_barrier(plbm_ctx* c)
+{
+    if (!c || !c->peers) return fail("plbm_peer_barrier: peer memory is not attached");
+    PeerFlags pf;
+    for (int s = 0; s < PLBM_MAX_RANKS; ++s) pf.f[s] = c->peer_flags[s];
+    ++c->epoch;
+    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(pf, c->cfg.rank, c->cfg.nranks, c->epoch, c->peer_timeout);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int plbm_peer_check(plbm_ctx* c)
+{
+    if (!c || !c->peers) return 0;
+    int t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, c->peer_timeout, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (t) return fail("a peer-memory barrier timed out: another slab's process stopped making progress");
+    return 0;
 }
 
 int plbm_exchange_info(plbm_ctx* c, plbm_exchange* o)

@@ -14,6 +14,13 @@ struct SlabTable {
     int nkl;                      // spectral columns owned by this rank
 };
 
+// Peer-memory transposes (several slabs, all GPUs of one node): instead of moving the half spectrum through two
+// all-to-alls, the column kernel reads every slab's share of its column straight from that slab's T1 over
+// NVLink and writes the result back there.  t1[s] is rank s's T1 = [NY/2+1][rows of s], mapped into this process.
+struct PeerTable {
+    cpx* t1[PLBM_MAX_RANKS];
+};
+
 struct PoissonFftDev {
     int n0, n1;          // n0 = NX "rows" of n1 = NY contiguous values (poisson.cpp:621-622)
     int nyl;             // local rows (n0 for a single slab)
@@ -30,7 +37,7 @@ struct PoissonFftDev {
 FftPlan make_fft_plan(int n, const cpx* tw);   // pass schedule for length n (radix schedule of oracle/fft_oracle.c, grouped)
 cudaError_t poisson_fft_configure(const PoissonFftDev& p);   // after row/col plans are set
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream);   // rho_q -> T1
-cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream);                            // T2 in place
+cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream, const PeerTable* peer = nullptr);   // T2 in place, or every slab's T1 through peer memory
 cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream);           // T1 -> phi
 cudaError_t launch_efield_periodic(const double* phi, const double* below, const double* above, double* Ex, double* Ey,
                                    int NX, int NYl, cudaStream_t stream);

@@ -61,6 +61,11 @@ class CudaSlabBackend:
         for name in ("plbm_halo_pack", "plbm_halo_unpack"):
             getattr(lib, name).argtypes = [C.c_void_p]
         lib.plbm_exchange_info.argtypes = [C.c_void_p, C.POINTER(PlbmExchange)]
+        lib.plbm_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+        lib.plbm_peer_attach.argtypes = [C.c_void_p, C.c_void_p]
+        lib.plbm_peer_barrier.argtypes = [C.c_void_p]
+        lib.plbm_peer_check.argtypes = [C.c_void_p]
+        lib.plbm_peer_detach.argtypes = [C.c_void_p]
         self.lib = lib
         x = PlbmExchange()
         _check(lib, lib.plbm_exchange_info(self.sim._h, C.byref(x)), "plbm_exchange_info")
@@ -95,6 +100,26 @@ class CudaSlabBackend:
     def poisson_stage(self, stage: int):
         _check(self.lib, self.lib.plbm_poisson_stage(self.sim._h, stage), "plbm_poisson_stage")
 
+    # peer-memory transposes (plbm.h: plbm_peer_*); PEER_BLOB_BYTES = PLBM_PEER_BLOB_BYTES
+    PEER_BLOB_BYTES = 256
+
+    def peer_export(self) -> bytes:
+        blob = C.create_string_buffer(self.PEER_BLOB_BYTES)
+        _check(self.lib, self.lib.plbm_peer_export(self.sim._h, blob), "plbm_peer_export")
+        return blob.raw
+
+    def peer_attach(self, blobs: bytes):
+        _check(self.lib, self.lib.plbm_peer_attach(self.sim._h, C.create_string_buffer(blobs, len(blobs))), "plbm_peer_attach")
+
+    def peer_barrier(self):
+        _check(self.lib, self.lib.plbm_peer_barrier(self.sim._h), "plbm_peer_barrier")
+
+    def peer_detach(self):
+        _check(self.lib, self.lib.plbm_peer_detach(self.sim._h), "plbm_peer_detach")
+
+    def peer_check(self):
+        _check(self.lib, self.lib.plbm_peer_check(self.sim._h), "plbm_peer_check")
+
     def stream_context(self):
         return self.torch.cuda.stream(self.stream)
 
@@ -112,7 +137,10 @@ class SlabDriver:
     """Sequences one time step over all slabs.  `backend` provides the per-slab kernels and the
     exchange buffers (torch tensors on the backend's device); `dist` is torch.distributed."""
 
-    def __init__(self, backend, group=None):
+    def __init__(self, backend, group=None, peer_memory=None):
+        """peer_memory: True = require the peer-memory transposes, False = all-to-alls through torch.distributed,
+        None = use peer memory when the backend offers it and every rank could attach (env PLBM_NO_PEER=1 disables)."""
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.b = backend
@@ -128,6 +156,48 @@ class SlabDriver:
         # all-to-all split sizes in doubles (complex = 2): T1 -> T2 and back
         self.t1_splits = [2 * (k0[d + 1] - k0[d]) * nyl for d in range(self.nranks)]
         self.t2_splits = [2 * nkl * (y0[s + 1] - y0[s]) for s in range(self.nranks)]
+        self.peer = False
+        if peer_memory is None:
+            peer_memory = None if os.environ.get("PLBM_NO_PEER", "0") in ("", "0") else False
+        if peer_memory is not False and backend.has_poisson and hasattr(backend, "peer_export"):
+            self.peer = self._attach_peers(required=bool(peer_memory))
+
+    def close(self):
+        """Collective: unmap the peers' memory on every rank before any rank frees its own (call before backend.close())."""
+        if self.peer:
+            self.b.peer_check()
+            self.b.peer_detach()
+            self.peer = False
+            self.dist.barrier(group=self.group)
+
+    def _attach_peers(self, required: bool) -> bool:
+        """Gather every rank's IPC blob and map the peers' spectra; all ranks agree on the outcome."""
+        import torch
+        b, d = self.b, self.dist
+        dev = b.stream.device
+        ok, blob, err = 1, bytes(b.PEER_BLOB_BYTES), ""
+        try:
+            blob = b.peer_export()
+        except PlbmError as e:
+            ok, err = 0, str(e)
+        mine = torch.tensor(list(blob) + [ok], dtype=torch.uint8, device=dev)
+        every = [torch.empty_like(mine) for _ in range(self.nranks)]
+        d.all_gather(every, mine, group=self.group)
+        every = [t.cpu().numpy().tobytes() for t in every]
+        if all(t[-1] for t in every):
+            try:
+                b.peer_attach(b"".join(t[:-1] for t in every))
+            except PlbmError as e:
+                ok, err = 0, str(e)
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        d.all_reduce(flag, op=d.ReduceOp.MIN, group=self.group)     # also orders the flag memset before any barrier
+        if int(flag.item()) == 0:
+            if required:
+                raise PlbmError(f"peer-memory transposes were required but are unavailable on rank {self.rank}: {err or 'a peer failed'}")
+            return False
+        return True
 
     def _sendrecv(self, send_up, send_down, recv_from_down, recv_from_up, wait=True):
         """What I send up is what my upper neighbour receives from below, and vice versa.  With two
@@ -166,9 +236,15 @@ class SlabDriver:
                 # spectral Poisson with two transposes
                 b.poisson_stage(0)
                 if b.has_poisson:
-                    d.all_to_all_single(b.t2, b.t1, self.t2_splits, self.t1_splits, group=self.group)
-                    b.poisson_stage(1)
-                    d.all_to_all_single(b.t1, b.t2, self.t1_splits, self.t2_splits, group=self.group)
+                    if self.peer:
+                        # the column pass works on every slab's T1 in place through peer memory (NVLink)
+                        b.peer_barrier()
+                        b.poisson_stage(4)
+                        b.peer_barrier()
+                    else:
+                        d.all_to_all_single(b.t2, b.t1, self.t2_splits, self.t1_splits, group=self.group)
+                        b.poisson_stage(1)
+                        d.all_to_all_single(b.t1, b.t2, self.t1_splits, self.t2_splits, group=self.group)
                     b.poisson_stage(2)
                     # my top phi row is the row below my upper neighbour's slab, my bottom row the one above my lower neighbour's
                     self._sendrecv(b.phi_last_row, b.phi_first_row, b.phi_below, b.phi_above)

@@ -347,7 +347,9 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
     achieved = K1_BYTES_PER_UPDATE * local_cells / (k1_ms * 1e-3) / 1e9
     line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, k1_ms, k1_ms * K / ms_total)
     line["roofline"]["note"] = "per GPU (slowest rank)"
-    line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + 2 all-to-all transposes of the half spectrum + 1 phi row per side"
+    transposes = ("column pass of the spectral solve reads/writes every slab's half spectrum in place through peer memory (NVLink), 2 flag barriers"
+                  if drv.peer else "2 all-to-all transposes of the half spectrum (NCCL)")
+    line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + {transposes} + 1 phi row per side"
     line["clocks"] = clocks.summary()
     line["gpu_launches"] = K * 8
     if not args.no_e2e:
@@ -374,6 +376,7 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
                        "d2h_bytes_per_step": NF * cells * 8, "steps": Ke,
                        "what": "initial state built on the device (plbm_initialize); per step the time step + download of every slab's 15 "
                                "visualised fields into pinned host memory (all ranks in parallel)"}
+    drv.close()
     b.close()
     if rank == 0:
         print(json.dumps(line), flush=True)

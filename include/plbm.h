@@ -176,6 +176,22 @@ int plbm_halo_unpack(plbm_ctx* ctx);
 int plbm_poisson_stage(plbm_ctx* ctx, int stage);
 int plbm_exchange_info(plbm_ctx* ctx, plbm_exchange* out);
 
+/* Peer-memory transposes (all slabs on GPUs of one node with peer access, one process per GPU).  Instead of the
+ * two all-to-alls, the column pass reads each slab's part of its spectral columns directly from that slab's T1
+ * over NVLink and writes the result back in place:
+ *   plbm_poisson_stage(0) -> plbm_peer_barrier -> plbm_poisson_stage(4) -> plbm_peer_barrier -> plbm_poisson_stage(2)
+ * Setup: every rank calls plbm_peer_export (a PLBM_PEER_BLOB_BYTES blob holding CUDA IPC handles), the host layer
+ * gathers the blobs of all ranks in rank order and hands them to plbm_peer_attach.  plbm_peer_barrier enqueues a
+ * barrier among all slabs' streams (flags in peer memory; it gives up after ~10 s and plbm_peer_check reports it).
+ * When attaching fails (no IPC / no peer access) the host layer keeps using the all-to-all path. */
+#define PLBM_PEER_BLOB_BYTES 256
+int plbm_peer_export(plbm_ctx* ctx, void* blob);
+int plbm_peer_attach(plbm_ctx* ctx, const void* blobs_of_all_ranks);
+int plbm_peer_barrier(plbm_ctx* ctx);
+int plbm_peer_check(plbm_ctx* ctx);
+/* Unmap the peers' memory.  Every rank must have detached (host-level barrier) before any rank destroys its context. */
+int plbm_peer_detach(plbm_ctx* ctx);
+
 /* Self-test hook: the library's fast division primitives on caller-supplied operands.
  * mode 0: a[i] / b[i] (data-dependent divisor); mode 1: a[i] / b[0] through the two-term 1/b[0] product (b[0] in {3,5,6});
  * mode 2: a[i] / b[0] through the device-refined reciprocal.  ok[i] = 1 when the operands were inside the domain where the

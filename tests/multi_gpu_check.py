@@ -21,10 +21,16 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     bad = 0
-    for NX, poisson, steps in ((64, "fft", 10), (60, "fft", 6), (48, "none", 5)):
+    require_peer = os.environ.get("PLBM_REQUIRE_PEER", "0") == "1"
+    # both transposes: all-to-alls through NCCL, and the column pass working in peer memory (auto: falls back when
+    # CUDA IPC / peer access is unavailable, unless PLBM_REQUIRE_PEER=1)
+    for NX, poisson, steps, peer in ((64, "fft", 10, False), (64, "fft", 10, None), (60, "fft", 6, None), (256, "fft", 12, None),
+                                     (48, "none", 5, None)):
         b = P.CudaSlabBackend(NX, NX, rank, world, poisson=poisson, device=local)
-        drv = P.SlabDriver(b)
+        drv = P.SlabDriver(b, peer_memory=(True if (require_peer and peer is None and poisson == "fft") else peer))
         drv.step(steps, want_fields=True)
+        if drv.peer:
+            b.peer_check()
         b.sync()
         full = drv.gather_fields(P.FIELD_NAMES)
         if rank == 0:
@@ -35,7 +41,9 @@ def main():
                 if not O.same_bits(full[n], want[n]):
                     bad += 1
                     print(f"MISMATCH world={world} {NX}x{NX}/{poisson}: {n} max|diff|={np.nanmax(np.abs(full[n] - want[n])):.3e}", flush=True)
-            print(f"checked {NX}x{NX}/{poisson}, {steps} steps on {world} GPUs: {'ok' if not bad else 'FAILED'}", flush=True)
+            print(f"checked {NX}x{NX}/{poisson}, {steps} steps on {world} GPUs, transposes through "
+                  f"{'peer memory' if drv.peer else 'all-to-all'}: {'ok' if not bad else 'FAILED'}", flush=True)
+        drv.close()
         b.close()
     flag = torch.tensor([bad], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
