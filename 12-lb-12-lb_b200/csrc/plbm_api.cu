@@ -24,6 +24,8 @@
 
 using namespace plbm;
 
+constexpr int PEER_NBUF = 6;              // buffers a slab exposes to its peers: T1, flags, halo_recv_lo, halo_recv_hi, phi_below, phi_above
+
 namespace {
 
 thread_local std::string g_err;
@@ -78,8 +80,8 @@ __global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags pf, int ra
 }
 
 struct PeerBlob {                       // what one rank tells the others (plbm_peer_export)
-    cudaIpcMemHandle_t t1, flags;
-    long long t1_offset, flags_offset;  // of the pointer inside the IPC-mapped allocation
+    cudaIpcMemHandle_t handle[PEER_NBUF];
+    long long offset[PEER_NBUF];        // of the pointer inside the IPC-mapped allocation
     int rank, nyl;
 };
 static_assert(sizeof(PeerBlob) <= PLBM_PEER_BLOB_BYTES, "PLBM_PEER_BLOB_BYTES too small");
@@ -132,7 +134,11 @@ struct plbm_ctx {
     PeerTable peer_t1 = {};
     unsigned long long* flags = nullptr;                 // [PLBM_MAX_RANKS] arrival counters written by the peers
     unsigned long long* peer_flags[PLBM_MAX_RANKS] = {};
-    void* peer_mapped[2 * PLBM_MAX_RANKS] = {};          // bases returned by cudaIpcOpenMemHandle
+    double* up_halo_recv_lo = nullptr;                   // upper neighbour's buffer for what arrives from below (= from me)
+    double* down_halo_recv_hi = nullptr;                 // lower neighbour's buffer for what arrives from above
+    double* up_phi_below = nullptr;                      // upper neighbour's copy of the row below its slab (= my last row)
+    double* down_phi_above = nullptr;
+    void* peer_mapped[PEER_NBUF * PLBM_MAX_RANKS] = {};  // bases returned by cudaIpcOpenMemHandle
     int* peer_timeout = nullptr;                         // device flag: a barrier gave up waiting
     unsigned long long epoch = 0;
     int slab_y0[PLBM_MAX_RANKS + 1] = {};
@@ -829,9 +835,11 @@ int plbm_peer_export(plbm_ctx* c, void* blob)
     }
     PeerBlob b;
     std::memset(&b, 0, sizeof(b));
-    CUDA_TRY(cudaIpcGetMemHandle(&b.t1, c->fft.T1));
-    CUDA_TRY(cudaIpcGetMemHandle(&b.flags, c->flags));
-    if (allocation_offset(c->fft.T1, &b.t1_offset) || allocation_offset(c->flags, &b.flags_offset)) return 1;
+    const void* bufs[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below, c->phi_above };
+    for (int i = 0; i < PEER_NBUF; ++i) {
+        CUDA_TRY(cudaIpcGetMemHandle(&b.handle[i], const_cast<void*>(bufs[i])));
+        if (allocation_offset(bufs[i], &b.offset[i])) return 1;
+    }
     b.rank = c->cfg.rank; b.nyl = c->geom.NYl;
     std::memset(blob, 0, PLBM_PEER_BLOB_BYTES);
     std::memcpy(blob, &b, sizeof(b));
@@ -843,29 +851,50 @@ int plbm_peer_attach(plbm_ctx* c, const void* blobs)
     if (!c || !blobs) return fail("plbm_peer_attach: null argument");
     if (!c->flags) return fail("plbm_peer_attach: call plbm_peer_export first");
     if (c->peers) return 0;
-    const int R = c->cfg.nranks;
+    const int R = c->cfg.nranks, me = c->cfg.rank, up = (me + 1) % R, down = (me + R - 1) % R;
     for (int s = 0; s < R; ++s) {
         PeerBlob b;
         std::memcpy(&b, (const char*)blobs + (size_t)s * PLBM_PEER_BLOB_BYTES, sizeof(b));
         if (b.rank != s || b.nyl != c->slab_y0[s + 1] - c->slab_y0[s]) return fail("plbm_peer_attach: blob %d does not describe slab %d", s, s);
-        if (s == c->cfg.rank) {
-            c->peer_t1.t1[s] = c->fft.T1;
-            c->peer_flags[s] = c->flags;
-            continue;
+        void* ptr[PEER_NBUF] = {};
+        if (s == me) {
+            void* mine[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below, c->phi_above };
+            for (int i = 0; i < PEER_NBUF; ++i) ptr[i] = mine[i];
+        } else {
+            for (int i = 0; i < PEER_NBUF; ++i) {
+                // buffers may share an underlying allocation (cudaMalloc sub-allocates): one mapping per distinct handle
+                void* base = nullptr;
+                for (int j = 0; j < i && !base; ++j)
+                    if (std::memcmp(&b.handle[i], &b.handle[j], sizeof(cudaIpcMemHandle_t)) == 0) base = (char*)ptr[j] - b.offset[j];
+                if (!base) {
+                    CUDA_TRY(cudaIpcOpenMemHandle(&base, b.handle[i], cudaIpcMemLazyEnablePeerAccess));
+                    c->peer_mapped[PEER_NBUF * s + i] = base;
+                }
+                ptr[i] = (char*)base + b.offset[i];
+            }
         }
-        void *t1 = nullptr, *fl = nullptr;
-        CUDA_TRY(cudaIpcOpenMemHandle(&t1, b.t1, cudaIpcMemLazyEnablePeerAccess));
-        c->peer_mapped[2 * s] = t1;
-        // T1 and the flags may live in the same underlying allocation: a second open of the same handle fails
-        if (std::memcmp(&b.t1, &b.flags, sizeof(cudaIpcMemHandle_t)) == 0) fl = t1;
-        else {
-            CUDA_TRY(cudaIpcOpenMemHandle(&fl, b.flags, cudaIpcMemLazyEnablePeerAccess));
-            c->peer_mapped[2 * s + 1] = fl;
-        }
-        c->peer_t1.t1[s] = (cpx*)((char*)t1 + b.t1_offset);
-        c->peer_flags[s] = (unsigned long long*)((char*)fl + b.flags_offset);
+        c->peer_t1.t1[s] = (cpx*)ptr[0];
+        c->peer_flags[s] = (unsigned long long*)ptr[1];
+        if (s == up) { c->up_halo_recv_lo = (double*)ptr[2]; c->up_phi_below = (double*)ptr[4]; }
+        if (s == down) { c->down_halo_recv_hi = (double*)ptr[3]; c->down_phi_above = (double*)ptr[5]; }
     }
     c->peers = true;
+    return 0;
+}
+
+// halo rows straight into the neighbours' receive buffers / boundary rows of phi into the neighbours' copies
+int plbm_halo_push(plbm_ctx* c)
+{
+    if (!c || !c->peers) return fail("plbm_halo_push: peer memory is not attached");
+    CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->down_halo_recv_hi, c->up_halo_recv_lo, c->geom, c->stream));
+    return 0;
+}
+int plbm_phi_rows_push(plbm_ctx* c)
+{
+    if (!c || !c->peers) return fail("plbm_phi_rows_push: peer memory is not attached");
+    const size_t row = sizeof(double) * c->cfg.NX;
+    CUDA_TRY(cudaMemcpyAsync(c->up_phi_below, c->phi + (size_t)(c->geom.NYl - 1) * c->cfg.NX, row, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->down_phi_above, c->phi, row, cudaMemcpyDeviceToDevice, c->stream));
     return 0;
 }
 

@@ -66,6 +66,8 @@ class CudaSlabBackend:
         lib.plbm_peer_barrier.argtypes = [C.c_void_p]
         lib.plbm_peer_check.argtypes = [C.c_void_p]
         lib.plbm_peer_detach.argtypes = [C.c_void_p]
+        lib.plbm_halo_push.argtypes = [C.c_void_p]
+        lib.plbm_phi_rows_push.argtypes = [C.c_void_p]
         self.lib = lib
         x = PlbmExchange()
         _check(lib, lib.plbm_exchange_info(self.sim._h, C.byref(x)), "plbm_exchange_info")
@@ -101,7 +103,7 @@ class CudaSlabBackend:
         _check(self.lib, self.lib.plbm_poisson_stage(self.sim._h, stage), "plbm_poisson_stage")
 
     # peer-memory transposes (plbm.h: plbm_peer_*); PEER_BLOB_BYTES = PLBM_PEER_BLOB_BYTES
-    PEER_BLOB_BYTES = 256
+    PEER_BLOB_BYTES = 512
 
     def peer_export(self) -> bytes:
         blob = C.create_string_buffer(self.PEER_BLOB_BYTES)
@@ -113,6 +115,12 @@ class CudaSlabBackend:
 
     def peer_barrier(self):
         _check(self.lib, self.lib.plbm_peer_barrier(self.sim._h), "plbm_peer_barrier")
+
+    def halo_push(self):
+        _check(self.lib, self.lib.plbm_halo_push(self.sim._h), "plbm_halo_push")
+
+    def phi_rows_push(self):
+        _check(self.lib, self.lib.plbm_phi_rows_push(self.sim._h), "plbm_phi_rows_push")
 
     def peer_detach(self):
         _check(self.lib, self.lib.plbm_peer_detach(self.sim._h), "plbm_peer_detach")
@@ -230,21 +238,29 @@ class SlabDriver:
                 if timing is not None:
                     e1.record()
                     timing.append((e0, e1))
+                if self.peer:
+                    # no messages at all: neighbours' buffers and every slab's half spectrum are written / read in
+                    # place through peer memory (NVLink), ordered by three flag barriers on the library's stream
+                    b.halo_push()
+                    b.poisson_stage(0)
+                    b.peer_barrier()
+                    b.halo_unpack()
+                    b.poisson_stage(4)
+                    b.peer_barrier()
+                    b.poisson_stage(2)
+                    b.phi_rows_push()
+                    b.peer_barrier()
+                    b.poisson_stage(3)
+                    continue
                 # halo: top row's upward populations go up, bottom row's downward populations go down
                 b.halo_pack()
                 pending = self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi, wait=False)
                 # spectral Poisson with two transposes
                 b.poisson_stage(0)
                 if b.has_poisson:
-                    if self.peer:
-                        # the column pass works on every slab's T1 in place through peer memory (NVLink)
-                        b.peer_barrier()
-                        b.poisson_stage(4)
-                        b.peer_barrier()
-                    else:
-                        d.all_to_all_single(b.t2, b.t1, self.t2_splits, self.t1_splits, group=self.group)
-                        b.poisson_stage(1)
-                        d.all_to_all_single(b.t1, b.t2, self.t1_splits, self.t2_splits, group=self.group)
+                    d.all_to_all_single(b.t2, b.t1, self.t2_splits, self.t1_splits, group=self.group)
+                    b.poisson_stage(1)
+                    d.all_to_all_single(b.t1, b.t2, self.t1_splits, self.t2_splits, group=self.group)
                     b.poisson_stage(2)
                     # my top phi row is the row below my upper neighbour's slab, my bottom row the one above my lower neighbour's
                     self._sendrecv(b.phi_last_row, b.phi_first_row, b.phi_below, b.phi_above)
@@ -258,6 +274,12 @@ class SlabDriver:
         them itself from the global initial condition, for which this is a no-op in effect)."""
         b = self.b
         with b.stream_context():
+            if self.peer:
+                b.peer_barrier()          # nobody is still unpacking an earlier exchange
+                b.halo_push()
+                b.peer_barrier()
+                b.halo_unpack()
+                return
             b.halo_pack()
             self._sendrecv(b.halo_send_hi, b.halo_send_lo, b.halo_recv_lo, b.halo_recv_hi)
             b.halo_unpack()

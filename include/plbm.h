@@ -184,11 +184,18 @@ int plbm_exchange_info(plbm_ctx* ctx, plbm_exchange* out);
  * gathers the blobs of all ranks in rank order and hands them to plbm_peer_attach.  plbm_peer_barrier enqueues a
  * barrier among all slabs' streams (flags in peer memory; it gives up after ~10 s and plbm_peer_check reports it).
  * When attaching fails (no IPC / no peer access) the host layer keeps using the all-to-all path. */
-#define PLBM_PEER_BLOB_BYTES 256
+#define PLBM_PEER_BLOB_BYTES 512
 int plbm_peer_export(plbm_ctx* ctx, void* blob);
 int plbm_peer_attach(plbm_ctx* ctx, const void* blobs_of_all_ranks);
 int plbm_peer_barrier(plbm_ctx* ctx);
 int plbm_peer_check(plbm_ctx* ctx);
+/* With peers attached the other two exchanges need no messages either: plbm_halo_push packs the outgoing
+ * population rows straight into the periodic neighbours' receive buffers (then barrier, plbm_halo_unpack), and
+ * plbm_phi_rows_push copies the slab's first/last row of phi into the neighbours' phi_above/phi_below (then
+ * barrier, plbm_poisson_stage(3)).  A whole step is then
+ *   step_local, halo_push, stage(0), BARRIER, halo_unpack, stage(4), BARRIER, stage(2), phi_rows_push, BARRIER, stage(3) */
+int plbm_halo_push(plbm_ctx* ctx);
+int plbm_phi_rows_push(plbm_ctx* ctx);
 /* Unmap the peers' memory.  Every rank must have detached (host-level barrier) before any rank destroys its context. */
 int plbm_peer_detach(plbm_ctx* ctx);
 
