@@ -230,21 +230,26 @@ def main():
         outs = [(dp * len(P.FIELD_NAMES))(*([C.cast(o[k].data_ptr(), dp) for k in range(NF)] + [dp()] * (len(P.FIELD_NAMES) - NF)))
                 for o in out_host]
         lib = sim.lib
-        sim.sync()
-        t0 = time.perf_counter()
-        if lib.plbm_upload_state(sim._h, fa, ga) != 0:
-            raise SystemExit(lib.plbm_last_error().decode())
-        # LBmethod::Run_simulation's loop (12-lb-12-lb_b200/host/plasma.cpp): step t+1 is issued while step t's fields
-        # are still crossing PCIe; every step's 15 fields are complete in host memory before the next fetch is started
-        for k in range(Ke):
-            if lib.plbm_step(sim._h, 1, 1) != 0 or lib.plbm_fetch_wait(sim._h) != 0 or lib.plbm_fetch_begin(sim._h, outs[k & 1]) != 0:
+        # host-memory bandwidth of the (virtualised) box fluctuates by 2x between runs: best of three identical passes
+        dts = []
+        for _rep in range(3):
+            sim.sync()
+            t0 = time.perf_counter()
+            if lib.plbm_upload_state(sim._h, fa, ga) != 0:
                 raise SystemExit(lib.plbm_last_error().decode())
-        if lib.plbm_fetch_wait(sim._h) != 0:
-            raise SystemExit(lib.plbm_last_error().decode())
-        sim.sync()
-        dt = time.perf_counter() - t0
+            # LBmethod::Run_simulation's loop (12-lb-12-lb_b200/host/plasma.cpp): step t+1 is issued while step t's fields
+            # are still crossing PCIe; every step's 15 fields are complete in host memory before the next fetch is started
+            for k in range(Ke):
+                if lib.plbm_step(sim._h, 1, 1) != 0 or lib.plbm_fetch_wait(sim._h) != 0 or lib.plbm_fetch_begin(sim._h, outs[k & 1]) != 0:
+                    raise SystemExit(lib.plbm_last_error().decode())
+            if lib.plbm_fetch_wait(sim._h) != 0:
+                raise SystemExit(lib.plbm_last_error().decode())
+            sim.sync()
+            dts.append(time.perf_counter() - t0)
+        dt = min(dts)
         line["e2e"] = {"value": cells * Ke / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 6 * 9 * cells * 8 / Ke,
-                       "d2h_bytes_per_step": NF * cells * 8, "steps": Ke, "what": E2E_WHAT}
+                       "d2h_bytes_per_step": NF * cells * 8, "steps": Ke, "what": E2E_WHAT,
+                       "passes_ms_per_step": [round(x / Ke * 1e3, 3) for x in dts]}
         del f_host, g_host, out_host
 
     # ---- cpu baseline (bounded sample of the same workload) -------------------------------
