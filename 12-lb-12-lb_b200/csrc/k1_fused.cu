@@ -192,10 +192,13 @@ __device__ __noinline__ void k1_cell_literal(const double* stash, double Ex, dou
 #define PLBM_K1_BOUNDS __launch_bounds__(K1_THREADS, PLBM_K1_MIN_BLOCKS)
 #endif
 
-template <bool WRITE_MACRO>
+// E_FROM_PHI: the field is not read from the Ex/Ey arrays but formed from the potential exactly as
+// poisson::ComputeElectricField_Periodic forms it (src/poisson.cpp:589-607) -- Exf is phi [NYl][NX], Eyf/Ezf the
+// neighbouring slabs' boundary rows (nullptr: wrap inside the array).  Saves the K3 sweep and 8 B per cell here.
+template <bool WRITE_MACRO, bool E_FROM_PHI>
 __global__ void PLBM_K1_BOUNDS
 k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
-                const double* __restrict__ Exf, const double* __restrict__ Eyf,
+                const double* __restrict__ Exf, const double* __restrict__ Eyf, const double* __restrict__ Ezf,
                 double* __restrict__ rho_q, const MacroOut mo,
                 const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g)
 {
@@ -232,7 +235,16 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
         }
     }
     const long long cidx = (long long)y * g.NX + x;    // scalar fields are flat x + NX*y
-    const double Ex = __ldg(Exf + cidx), Ey = __ldg(Eyf + cidx);
+    double Ex, Ey;
+    if constexpr (E_FROM_PHI) {
+        const double* row = Exf + (long long)y * g.NX;
+        const double* below = (y > 0) ? row - g.NX : (Eyf ? Eyf : Exf + (long long)(g.NYl - 1) * g.NX);
+        const double* above = (y < g.NYl - 1) ? row + g.NX : (Ezf ? Ezf : Exf);
+        Ex = __dmul_rn(-0.5, __dsub_rn(__ldg(row + xp), __ldg(row + xm)));
+        Ey = __dmul_rn(-0.5, __dsub_rn(__ldg(above + x), __ldg(below + x)));
+    } else {
+        Ex = __ldg(Exf + cidx); Ey = __ldg(Eyf + cidx);
+    }
 
     K1Out o;
     o.dst = dst + (long long)r0o + x;
@@ -254,21 +266,33 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
 
 static constexpr size_t k1_smem_bytes() { return sizeof(double) * NPLANES * K1_THREADS; }
 
-cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,
-                            const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
+template <bool M, bool P>
+static cudaError_t k1_launch(const double* src, double* dst, const double* a, const double* b, const double* e, double* rho_q,
+                             const MacroOut& mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k1_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k1_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
-        if (e != cudaSuccess) return e;
+        cudaError_t err = cudaFuncSetAttribute(k1_fused_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
+        if (err != cudaSuccess) return err;
         configured = true;
     }
     dim3 grid((g.NX + K1_THREADS - 1) / K1_THREADS, g.NYl);
-    if (mo) k1_fused_kernel<true><<<grid, K1_THREADS, k1_smem_bytes(), stream>>>(src, dst, Ex, Ey, rho_q, *mo, c, g);
-    else    k1_fused_kernel<false><<<grid, K1_THREADS, k1_smem_bytes(), stream>>>(src, dst, Ex, Ey, rho_q, MacroOut{}, c, g);
+    k1_fused_kernel<M, P><<<grid, K1_THREADS, k1_smem_bytes(), stream>>>(src, dst, a, b, e, rho_q, mo, c, g);
     return cudaGetLastError();
+}
+
+cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,
+                            const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
+{
+    if (mo) return k1_launch<true, false>(src, dst, Ex, Ey, nullptr, rho_q, *mo, c, g, stream);
+    return k1_launch<false, false>(src, dst, Ex, Ey, nullptr, rho_q, MacroOut{}, c, g, stream);
+}
+
+cudaError_t launch_k1_fused_phi(const double* src, double* dst, const double* phi, const double* below, const double* above, double* rho_q,
+                                const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
+{
+    if (mo) return k1_launch<true, true>(src, dst, phi, below, above, rho_q, *mo, c, g, stream);
+    return k1_launch<false, true>(src, dst, phi, below, above, rho_q, MacroOut{}, c, g, stream);
 }
 
 } // namespace plbm

@@ -17,4 +17,9 @@ struct MacroOut {
 cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,
                             const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
 
+// same step with E = -grad(phi) formed inside the kernel (periodic central differences, bit-identical to K3);
+// below/above: boundary rows of phi owned by the neighbouring slabs, nullptr on a single slab
+cudaError_t launch_k1_fused_phi(const double* src, double* dst, const double* phi, const double* below, const double* above, double* rho_q,
+                                const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
+
 } // namespace plbm

@@ -122,6 +122,7 @@ struct plbm_ctx {
     bool fetch_pending = false;
     double* staging = nullptr;               // 9*NX*NYl doubles for AoS transfers
     bool macro_valid = false;
+    bool e_stale = false;                    // Ex/Ey arrays not materialised: K1 takes E = -grad(phi) from phi itself (fused periodic FFT path)
     bool poisson_called = false;             // call_once of reference src/poisson.cpp:34-41
     // spectral Poisson
     PoissonFftDev fft = {};
@@ -318,6 +319,25 @@ int solve_poisson(plbm_ctx* c, long long* launches)
     return poisson_efield(c, bc, launches);
 }
 
+// Ex/Ey as arrays, for everything that is not K1 (downloads, host API, walls)
+int materialise_efield(plbm_ctx* c, long long* launches = nullptr)
+{
+    if (!c->e_stale) return 0;
+    c->e_stale = false;
+    return poisson_efield(c, PLBM_BC_PERIODIC, launches);
+}
+
+// the time loop's SolvePoisson: on the fused periodic spectral path the field stays implicit in phi
+int solve_poisson_in_loop(plbm_ctx* c, long long* launches)
+{
+    const bool implicit = !c->unfused && c->pop[0] && c->cfg.poisson_type == PLBM_POISSON_FFT && c->cfg.bc_type == PLBM_BC_PERIODIC;
+    if (!implicit) return solve_poisson(c, launches);
+    if (poisson_first_call(c)) return 1;
+    if (poisson_solver(c, PLBM_POISSON_FFT, launches)) return 1;
+    c->e_stale = true;
+    return 0;
+}
+
 int one_step(plbm_ctx* c, bool want_fields, long long* launches)
 {
     if (c->unfused) {
@@ -349,8 +369,14 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
         mo.ux[s] = c->macro[2 * s]; mo.uy[s] = c->macro[2 * s + 1];
         mo.T[s] = c->macro[6 + s]; mo.rho[s] = c->macro[9 + s];
     }
-    CUDA_TRY(launch_k1_fused(c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->rho_q, want_fields ? &mo : nullptr,
-                             c->consts, c->geom, c->stream));
+    if (c->e_stale) {
+        const bool slabs = c->cfg.nranks > 1;
+        CUDA_TRY(launch_k1_fused_phi(c->pop[c->cur], c->pop[c->cur ^ 1], c->phi, slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr,
+                                     c->rho_q, want_fields ? &mo : nullptr, c->consts, c->geom, c->stream));
+    } else {
+        CUDA_TRY(launch_k1_fused(c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->rho_q, want_fields ? &mo : nullptr,
+                                 c->consts, c->geom, c->stream));
+    }
     if (launches) *launches += 1;
     c->cur ^= 1;
     c->macro_valid = want_fields;
@@ -518,6 +544,7 @@ int plbm_initialize(plbm_ctx* c)
         for (int k = 0; k < 3; ++k) CUDA_TRY(cudaMemsetAsync(c->pa.tmp[k], 0, sizeof(double) * n * NQ, c->stream));   // std::vector::resize zero-fills temp_*
         CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
         CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
+        c->e_stale = false;
         CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
         CUDA_TRY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
         c->poisson_called = false;
@@ -531,6 +558,7 @@ int plbm_initialize(plbm_ctx* c)
     CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
     CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
     CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
+    c->e_stale = false;
     CUDA_TRY(cudaMemsetAsync(c->phi, 0, sizeof(double) * n, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
     c->poisson_called = false;
@@ -593,6 +621,7 @@ int plbm_set_efield(plbm_ctx* c, const double* Ex, const double* Ey)
 {
     if (!c || !Ex || !Ey) return fail("plbm_set_efield: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
+    c->e_stale = false;
     CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -605,8 +634,9 @@ int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
     if (c->cfg.nranks > 1) return fail("plbm_step: this context is one slab of %d; drive it with plbm_step_local / plbm_halo_* / plbm_poisson_stage", c->cfg.nranks);
     for (int t = 0; t < nsteps; ++t) {
         if (one_step(c, want_fields && t == nsteps - 1, nullptr)) return 1;
-        if (solve_poisson(c, nullptr)) return 1;
+        if (solve_poisson_in_loop(c, nullptr)) return 1;
     }
+    if (want_fields && materialise_efield(c)) return 1;
     return 0;
 }
 
@@ -620,6 +650,7 @@ int plbm_sync(plbm_ctx* c)
 int plbm_download_fields(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 {
     if (!c || !out) return fail("plbm_download_fields: null argument");
+    if ((out[PLBM_F_EX] || out[PLBM_F_EY]) && materialise_efield(c)) return 1;
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     for (int k = 0; k < PLBM_NUM_FIELDS; ++k) {
         if (!out[k]) continue;
@@ -641,6 +672,7 @@ int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 {
     if (!c || !out) return fail("plbm_fetch_begin: null argument");
     if (c->fetch_pending) return fail("plbm_fetch_begin: the previous fetch was not completed with plbm_fetch_wait");
+    if ((out[PLBM_F_EX] || out[PLBM_F_EY]) && materialise_efield(c)) return 1;
     const size_t n = (size_t)c->geom.NX * c->geom.NYl, bytes = sizeof(double) * n;
     if (!c->copy_stream) {                                 // first use: second macro set, snapshot buffers, copy stream
         CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -712,7 +744,8 @@ int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, f
     for (int t = 0; t < nsteps; ++t) {
         if (one_step(c, want_fields && t == nsteps - 1, &nl)) return 1;
         CUDA_TRY(cudaEventRecord(c->events[2 * t + 1], c->stream));
-        if (solve_poisson(c, &nl)) return 1;
+        if (solve_poisson_in_loop(c, &nl)) return 1;
+        if (want_fields && t == nsteps - 1 && materialise_efield(c, &nl)) return 1;
         CUDA_TRY(cudaEventRecord(c->events[2 * t + 2], c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -736,6 +769,7 @@ int plbm_host_solve_poisson(plbm_ctx* c, const double* rho_q, double* Ex, double
     if (!c || !rho_q || !Ex || !Ey) return fail("plbm_host_solve_poisson: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     CUDA_TRY(cudaMemcpyAsync(c->rho_q, rho_q, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->e_stale = false;
     CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
     if (solve_poisson(c, nullptr)) return 1;
@@ -761,6 +795,7 @@ int plbm_host_efield(plbm_ctx* c, int bc_type, double* Ex, double* Ey)
     if (!c || !Ex || !Ey) return fail("plbm_host_efield: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     if (poisson_first_call(c)) return 1;
+    c->e_stale = false;
     CUDA_TRY(cudaMemcpyAsync(c->Ex, Ex, bytes, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->Ey, Ey, bytes, cudaMemcpyHostToDevice, c->stream));
     if (poisson_efield(c, bc_type, nullptr)) return 1;
@@ -814,7 +849,10 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
     case 0: CUDA_TRY(launch_poisson_rows_fwd(c->fft, c->rho_q, c->stream)); return 0;
     case 1: CUDA_TRY(launch_poisson_cols(c->fft, c->stream)); return 0;
     case 2: CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream)); return 0;
-    case 3: return poisson_efield(c, PLBM_BC_PERIODIC, nullptr);
+    case 3:                                  // field reconstruction: implicit in phi for K1, materialised on demand
+        if (c->unfused || !c->pop[0]) return poisson_efield(c, PLBM_BC_PERIODIC, nullptr);
+        c->e_stale = true;
+        return 0;
     case 4:
         if (!c->peers) return fail("plbm_poisson_stage(4): peer memory is not attached (plbm_peer_attach)");
         CUDA_TRY(launch_poisson_cols(c->fft, c->stream, &c->peer_t1));

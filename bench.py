@@ -9,7 +9,7 @@ Workload at N=1: BASELINE.json configs[2], 2048x2048, FFT Poisson, periodic -- t
 the single-GPU roofline number is quoted on (the state, 2 x 1.8 GB, is far larger than L2).
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      K1 (fused collide-stream) against the measured HBM copy peak; 888 algorithmic B/update
+  roofline      K1 (fused collide-stream) against the measured HBM copy peak; 880 algorithmic B/update
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/ref_plasma_timing) on the host cores, bounded sample
   e2e           same metric through the public API with HOST buffers: initial state uploaded from pinned
                 memory, the 15 visualised fields fetched to pinned memory every step (copy of step t overlapped with step t+1)
@@ -29,8 +29,8 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-K1_BYTES_PER_UPDATE = 888          # 54*8 read + 54*8 write + Ex,Ey 16 + rho_q 8   
-STEP_BYTES_PER_UPDATE = 960        # + Poisson passes 48 + field 24
+K1_BYTES_PER_UPDATE = 880          # 54*8 read + 54*8 write + phi 8 (E = -grad phi is formed in the kernel) + rho_q 8   
+STEP_BYTES_PER_UPDATE = 928        # + Poisson passes 3 x (8 + 8); SURVEY.md 8d's 960 minus the E-field sweep that no longer exists
 FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback
 
 
