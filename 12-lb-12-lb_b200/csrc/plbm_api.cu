@@ -849,6 +849,10 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
     case 0: CUDA_TRY(launch_poisson_rows_fwd(c->fft, c->rho_q, c->stream)); return 0;
     case 1: CUDA_TRY(launch_poisson_cols(c->fft, c->stream)); return 0;
     case 2: CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream)); return 0;
+    case 5:                                  // stage 2 + the boundary rows of phi written into the neighbours as well (peer memory)
+        if (!c->peers) return fail("plbm_poisson_stage(5): peer memory is not attached (plbm_peer_attach)");
+        CUDA_TRY(launch_poisson_rows_inv(c->fft, c->phi, c->stream, c->down_phi_above, c->up_phi_below));
+        return 0;
     case 3:                                  // field reconstruction: implicit in phi for K1, materialised on demand
         if (c->unfused || !c->pop[0]) return poisson_efield(c, PLBM_BC_PERIODIC, nullptr);
         c->e_stale = true;

@@ -139,20 +139,27 @@ poisson_cols_kernel(cpx* T, const __grid_constant__ FftPlan plan,
     fft_run<+1, TAIL, ODD>(plan, fbuf, sm, col);
 }
 
+// copya / copyb: second destination of the row (a neighbouring slab's copy of my boundary row, in peer memory), or nullptr
 struct RowPairOut {
-    double* rowa; double* rowb; bool paired; double norm;
+    double* rowa; double* rowb; bool paired; double norm; double* copya; double* copyb;
     static constexpr bool is_smem = false;
     __device__ __forceinline__ void store(int j, cpx z) const
     {
-        rowa[j] = __dmul_rn(z.re, norm);                        // poisson.cpp:415-419
-        if (paired) rowb[j] = __dmul_rn(z.im, norm);
+        const double a = __dmul_rn(z.re, norm);                 // poisson.cpp:415-419
+        rowa[j] = a;
+        if (copya) copya[j] = a;
+        if (paired) {
+            const double b = __dmul_rn(z.im, norm);
+            rowb[j] = b;
+            if (copyb) copyb[j] = b;
+        }
     }
 };
 
 template <int FFT_CAP, int TAIL, int ODD>
 __global__ void __launch_bounds__(FFT_CAP, 1)
 poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, const __grid_constant__ FftPlan plan,
-                        int n0, int n1, int nh, double norm)
+                        int n0, int n1, int nh, double norm, double* first_row_copy, double* last_row_copy)
 {
     extern __shared__ cpx fbuf[];
     const int ra = 2 * blockIdx.x, rb = ra + 1;
@@ -174,7 +181,11 @@ poisson_rows_inv_kernel(const cpx* __restrict__ T, double* __restrict__ phi, con
         if (!self_conj) sm.store(n1 - k, { __dadd_rn(ar, bi), __dsub_rn(br, ai) });
     }
     __syncthreads();
-    const RowPairOut dst{ phi + (size_t)ra * n1, phi + (size_t)rb * n1, paired, norm };
+    // the slab's first row goes to the lower neighbour as "the row above it", the last row to the upper neighbour
+    const int last = n0 - 1;
+    const RowPairOut dst{ phi + (size_t)ra * n1, phi + (size_t)rb * n1, paired, norm,
+                          ra == 0 ? first_row_copy : (ra == last ? last_row_copy : nullptr),
+                          (paired && rb == last) ? last_row_copy : nullptr };
     fft_run<+1, TAIL, ODD>(plan, fbuf, sm, dst);
 }
 
@@ -298,13 +309,13 @@ cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream, con
         return cudaGetLastError();
     });
 }
-cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream)
+cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream, double* first_row_copy, double* last_row_copy)
 {
     const int nh = p.n1 / 2 + 1, t = p.row.threads, grid = (p.nyl + 1) / 2;
     const size_t sm = fft_smem_bytes(p.n1);
     return with_shape(p.row, [&](auto CAP, auto TAIL, auto ODD) {
         poisson_rows_inv_kernel<decltype(CAP)::value, decltype(TAIL)::value, decltype(ODD)::value>
-            <<<grid, t, sm, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm);
+            <<<grid, t, sm, stream>>>(p.T1, phi, p.row, p.nyl, p.n1, nh, p.norm, first_row_copy, last_row_copy);
         return cudaGetLastError();
     });
 }

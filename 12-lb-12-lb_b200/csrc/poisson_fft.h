@@ -38,7 +38,8 @@ FftPlan make_fft_plan(int n, const cpx* tw);   // pass schedule for length n (ra
 cudaError_t poisson_fft_configure(const PoissonFftDev& p);   // after row/col plans are set
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream);   // rho_q -> T1
 cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream, const PeerTable* peer = nullptr);   // T2 in place, or every slab's T1 through peer memory
-cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream);           // T1 -> phi
+cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream,
+                                    double* first_row_copy = nullptr, double* last_row_copy = nullptr);           // T1 -> phi
 cudaError_t launch_efield_periodic(const double* phi, const double* below, const double* above, double* Ex, double* Ey,
                                    int NX, int NYl, cudaStream_t stream);
 

@@ -247,8 +247,7 @@ class SlabDriver:
                     b.halo_unpack()
                     b.poisson_stage(4)
                     b.peer_barrier()
-                    b.poisson_stage(2)
-                    b.phi_rows_push()
+                    b.poisson_stage(5)        # P3, boundary rows of phi stored into the neighbours as well
                     b.peer_barrier()
                     b.poisson_stage(3)
                     continue

@@ -193,7 +193,15 @@ int plbm_peer_check(plbm_ctx* ctx);
  * population rows straight into the periodic neighbours' receive buffers (then barrier, plbm_halo_unpack), and
  * plbm_phi_rows_push copies the slab's first/last row of phi into the neighbours' phi_above/phi_below (then
  * barrier, plbm_poisson_stage(3)).  A whole step is then
- *   step_local, halo_push, stage(0), BARRIER, halo_unpack, stage(4), BARRIER, stage(2), phi_rows_push, BARRIER, stage(3) */
+ *   step_local, halo_push, stage(0), BARRIER, halo_unpack, stage(4), BARRIER, stage(5), BARRIER, stage(3)
+ * where stage(5) = stage(2) whose last pass also stores the boundary rows into the neighbours (plbm_phi_rows_push is
+ * the same transfer as two copies, for callers that keep stage(2)).
+ * Hazards across steps: a rank passes barrier n only after every rank has enqueued-and-finished everything before
+ * its own barrier n.  Writes into a peer (halo rows, phi rows, T1 columns in stage 4) always follow a barrier that the
+ * peer reaches after its last read of the previous contents: halo buffers are read by halo_unpack (before the 2nd
+ * barrier of a step) and rewritten after the 3rd; T1 is read by the peers' stage 4 (before the 2nd barrier) and
+ * rewritten by stage 0 of the next step; phi copies are read by K1 / stage 3 (before the next step's 1st barrier) and
+ * rewritten after its 2nd. */
 int plbm_halo_push(plbm_ctx* ctx);
 int plbm_phi_rows_push(plbm_ctx* ctx);
 /* Unmap the peers' memory.  Every rank must have detached (host-level barrier) before any rank destroys its context. */
