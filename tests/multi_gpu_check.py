@@ -24,7 +24,7 @@ def main():
     require_peer = os.environ.get("PLBM_REQUIRE_PEER", "0") == "1"
     # both transposes: all-to-alls through NCCL, and the column pass working in peer memory (auto: falls back when
     # CUDA IPC / peer access is unavailable, unless PLBM_REQUIRE_PEER=1)
-    for NX, poisson, steps, peer in ((64, "fft", 10, False), (64, "fft", 10, None), (60, "fft", 6, None), (256, "fft", 12, None),
+    for NX, poisson, steps, peer in ((64, "fft", 10, False), (64, "fft", 10, None), (60, "fft", 6, None), (256, "fft", 12, None), (1536, "fft", 3, None),
                                      (48, "none", 5, None)):
         b = P.CudaSlabBackend(NX, NX, rank, world, poisson=poisson, device=local)
         drv = P.SlabDriver(b, peer_memory=(True if (require_peer and peer is None and poisson == "fft") else peer))
