@@ -112,6 +112,7 @@ class CudaSlabBackend:
 
     def peer_attach(self, blobs: bytes):
         _check(self.lib, self.lib.plbm_peer_attach(self.sim._h, C.create_string_buffer(blobs, len(blobs))), "plbm_peer_attach")
+        self._peers_attached = True
 
     def peer_barrier(self):
         _check(self.lib, self.lib.plbm_peer_barrier(self.sim._h), "plbm_peer_barrier")
@@ -124,6 +125,7 @@ class CudaSlabBackend:
 
     def peer_detach(self):
         _check(self.lib, self.lib.plbm_peer_detach(self.sim._h), "plbm_peer_detach")
+        self._peers_attached = False
 
     def peer_check(self):
         _check(self.lib, self.lib.plbm_peer_check(self.sim._h), "plbm_peer_check")
@@ -136,6 +138,8 @@ class CudaSlabBackend:
 
     def sync(self):
         self.sim.sync()
+        if getattr(self, "_peers_attached", False):
+            self.peer_check()          # a barrier that gave up (dead peer) must not pass silently
 
     def close(self):
         self.sim.close()
