@@ -11,6 +11,10 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 
 # order of visualize::UpdateVisualization's parameters (reference include/visualize.hpp:53-61) + phi
+NUM_FRAMES, NUM_SERIES, NUM_POINTS = 12, 19, 9          # plbm.h: PLBM_NUM_FRAMES / SERIES / POINTS
+FRAME_NAMES = ("rho_e", "rho_i", "rho_q", "ux_e", "uy_e", "ue_mag", "ux_i", "uy_i", "ui_mag", "T_e", "T_i", "T_n")
+SERIES_NAMES = ("ux_e", "uy_e", "ue_mag", "ux_i", "uy_i", "ui_mag", "ux_n", "uy_n", "un_mag", "T_e", "T_i", "T_n",
+                "rho_e", "rho_i", "rho_n", "rho_q", "Ex", "Ey", "E_mag")
 FIELD_NAMES = ("ux_e", "uy_e", "ux_i", "uy_i", "ux_n", "uy_n", "T_e", "T_i", "T_n",
                "rho_e", "rho_i", "rho_n", "rho_q", "Ex", "Ey", "phi")
 POISSON = {"none": 0, "gs": 1, "sor": 2, "fft": 3, "nps": 4}   # poisson::PoissonType, reference include/poisson.hpp:15-21
@@ -73,6 +77,7 @@ def load_library() -> C.CDLL:
     lib.plbm_download_fields.argtypes = [C.c_void_p, C.POINTER(dp)]
     lib.plbm_fetch_begin.argtypes = [C.c_void_p, C.POINTER(dp)]
     lib.plbm_fetch_wait.argtypes = [C.c_void_p]
+    lib.plbm_frames_begin.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float)), dp]
     lib.plbm_pin_host.argtypes = [C.c_void_p, C.c_size_t]
     lib.plbm_unpin_host.argtypes = [C.c_void_p]
     lib.plbm_host_solve_poisson.argtypes = [C.c_void_p, dp, dp, dp]
@@ -220,6 +225,23 @@ class PlasmaLBM:
             ptrs[k] = _dptr(out[k]) if k < nfields else dp()
         self._fetch_target = out                     # keep the destination alive until fetch_wait
         _check(self.lib, self.lib.plbm_fetch_begin(self._h, ptrs), "plbm_fetch_begin")
+
+    def frames_begin(self, frames: np.ndarray | None, series: np.ndarray | None):
+        """Alternate output path (plbm_frames_begin): frames[12, NY_local, NX] float32 and/or series[19, 9] float64
+        receive what the visualiser derives from the last step's fields; complete with fetch_wait()."""
+        fp = C.POINTER(C.c_float)
+        ptrs = None
+        if frames is not None:
+            if frames.dtype != np.float32 or not frames.flags["C_CONTIGUOUS"] or frames.shape != (NUM_FRAMES, self.NY_local, self.NX):
+                raise ValueError("frames_begin: frames must be a C-contiguous float32 array [12, NY_local, NX]")
+            ptrs = (fp * NUM_FRAMES)(*[frames[k].ctypes.data_as(fp) for k in range(NUM_FRAMES)])
+        sp = None
+        if series is not None:
+            if series.dtype != np.float64 or not series.flags["C_CONTIGUOUS"] or series.shape != (NUM_SERIES, NUM_POINTS):
+                raise ValueError("frames_begin: series must be a C-contiguous float64 array [19, 9]")
+            sp = _dptr(series)
+        self._fetch_target = (frames, series)
+        _check(self.lib, self.lib.plbm_frames_begin(self._h, ptrs, sp), "plbm_frames_begin")
 
     def fetch_wait(self):
         _check(self.lib, self.lib.plbm_fetch_wait(self._h), "plbm_fetch_wait")

@@ -18,6 +18,7 @@
 #include "k1_fused.h"
 #include "layout.h"
 #include "lbm_consts.h"
+#include "output.h"
 #include "phases.h"
 #include "poisson_fft.h"
 #include "poisson_iter.h"
@@ -120,6 +121,8 @@ struct plbm_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_snap = nullptr, ev_fetched = nullptr;
     bool fetch_pending = false;
+    float* frames = nullptr;                 // alternate output path: NUM_FRAMES planes of floats
+    double* series = nullptr;                // [NUM_SERIES][NUM_POINTS]
     double* staging = nullptr;               // 9*NX*NYl doubles for AoS transfers
     bool macro_valid = false;
     bool e_stale = false;                    // Ex/Ey arrays not materialised: K1 takes E = -grad(phi) from phi itself (fused periodic FFT path)
@@ -520,6 +523,7 @@ void plbm_destroy(plbm_ctx* c)
     cudaFree(c->flags); cudaFree(c->peer_timeout);
     for (int b = 0; b < 2; ++b) for (int k = 0; k < 12; ++k) cudaFree(c->macro_sets[b][k]);
     for (int k = 0; k < 4; ++k) cudaFree(c->snap[k]);
+    cudaFree(c->frames); cudaFree(c->series);
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     if (c->ev_fetched) cudaEventDestroy(c->ev_fetched);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -702,6 +706,47 @@ int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
     if (c->unfused && any_macro)                           // single moment set on this path: the next sweep waits for the copy
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_fetched, 0));
     c->fetch_pending = true;
+    return 0;
+}
+
+int plbm_frames_begin(plbm_ctx* c, float* const frames[PLBM_NUM_FRAMES], double* series)
+{
+    if (!c) return fail("plbm_frames_begin: null context");
+    if (c->fetch_pending) return fail("plbm_frames_begin: the previous fetch was not completed");
+    if (!c->macro_valid) return fail("plbm_frames_begin: moment fields were not requested from the last plbm_step");
+    const size_t n = (size_t)c->geom.NX * c->geom.NYl;
+    if (!c->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
+    }
+    if (!c->frames) {
+        if (dev_alloc(c, &c->frames, n * NUM_FRAMES)) return 1;
+        if (dev_alloc(c, &c->series, (size_t)NUM_SERIES * NUM_POINTS)) return 1;
+    }
+    // narrowing runs on the compute stream right after the step, so the next step may overwrite every field
+    if (frames) {
+        const FrameFields f = { c->macro[PLBM_F_RHO_E], c->macro[PLBM_F_RHO_I], c->rho_q, c->macro[PLBM_F_UX_E], c->macro[PLBM_F_UY_E],
+                                c->macro[PLBM_F_UX_I], c->macro[PLBM_F_UY_I], c->macro[PLBM_F_T_E], c->macro[PLBM_F_T_I], c->macro[PLBM_F_T_N] };
+        CUDA_TRY(launch_frames(f, c->frames, n, c->stream));
+    }
+    if (series) {
+        if (materialise_efield(c)) return 1;
+        SeriesFields f;
+        for (int s = 0; s < 3; ++s) {
+            f.ux[s] = c->macro[2 * s]; f.uy[s] = c->macro[2 * s + 1]; f.T[s] = c->macro[6 + s]; f.rho[s] = c->macro[9 + s];
+        }
+        f.rho_q = c->rho_q; f.Ex = c->Ex; f.Ey = c->Ey;
+        CUDA_TRY(launch_series(f, c->series, c->cfg.NX, c->cfg.NY, c->cfg.y0, c->geom.NYl, c->stream));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_snap, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_snap, 0));
+    if (frames)
+        for (int k = 0; k < NUM_FRAMES; ++k)
+            if (frames[k]) CUDA_TRY(cudaMemcpyAsync(frames[k], c->frames + (size_t)k * n, sizeof(float) * n, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (series) CUDA_TRY(cudaMemcpyAsync(series, c->series, sizeof(double) * NUM_SERIES * NUM_POINTS, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->ev_fetched, c->copy_stream));
+    c->fetch_pending = true;                                   // one frame buffer: the next narrowing comes after plbm_fetch_wait
     return 0;
 }
 

@@ -3,10 +3,16 @@
 // body itself (UpdateMacro, ComputeEquilibrium, Collide, Stream, SolvePoisson) runs on the device.
 #include "plasma.hpp"
 #include "plbm.h"
+#include "visualize_frames.hpp"
 
 #include <iostream>
 #include <stdexcept>
 #include <string>
+
+// optional: only a visualiser that implements the alternate entry defines it (the reference's visualize.cpp does not)
+namespace visualize {
+void UpdateVisualizationFrames(int, int, int, const float* const[VF_COUNT], const double[VS_COUNT][9]) __attribute__((weak));
+}
 
 namespace {
 [[noreturn]] void raise(const char* what)
@@ -110,6 +116,44 @@ void LBmethod::Run_simulation()
                                        fields_[PLBM_F_RHO_E], fields_[PLBM_F_RHO_I], fields_[PLBM_F_RHO_N],
                                        fields_[PLBM_F_RHO_Q], fields_[PLBM_F_EX], fields_[PLBM_F_EY]);
     }
+    visualize::CloseVisualization();
+    std::cout << "Simulation ended " << std::endl;
+}
+
+void LBmethod::Run_simulation_frames()
+{
+    if (!visualize::UpdateVisualizationFrames)
+        throw std::runtime_error("LBmethod::Run_simulation_frames: the linked visualiser does not implement visualize::UpdateVisualizationFrames");
+    visualize::InitVisualization(NX, NY, NSTEPS);
+    const size_t n = static_cast<size_t>(NX) * NY;
+    // two host sets: the one being drawn and the one being filled by the copy stream
+    std::vector<float> mats[2][PLBM_NUM_FRAMES];
+    std::vector<double> series[2];
+    for (int b = 0; b < 2; ++b) {
+        for (auto& m : mats[b]) { m.assign(n, 0.0f); plbm_pin_host(m.data(), sizeof(float) * n); }
+        series[b].assign(static_cast<size_t>(PLBM_NUM_SERIES) * PLBM_NUM_POINTS, 0.0);
+    }
+    auto begin = [&](int b) {
+        float* out[PLBM_NUM_FRAMES];
+        for (int k = 0; k < PLBM_NUM_FRAMES; ++k) out[k] = mats[b][k].data();
+        if (plbm_frames_begin(ctx_, out, series[b].data())) raise("LBmethod: frame fetch");
+    };
+    if (NSTEPS > 0) {
+        if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+        begin(0);
+    }
+    for (int t = 0; t < NSTEPS; ++t) {
+        const int cur = t & 1;
+        if (plbm_fetch_wait(ctx_)) raise("LBmethod: frame fetch");
+        if (t + 1 < NSTEPS) {
+            if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+            begin(cur ^ 1);
+        }
+        const float* m[PLBM_NUM_FRAMES];
+        for (int k = 0; k < PLBM_NUM_FRAMES; ++k) m[k] = mats[cur][k].data();
+        visualize::UpdateVisualizationFrames(t, NX, NY, m, reinterpret_cast<const double (*)[PLBM_NUM_POINTS]>(series[cur].data()));
+    }
+    for (int b = 0; b < 2; ++b) for (auto& m : mats[b]) plbm_unpin_host(m.data());
     visualize::CloseVisualization();
     std::cout << "Simulation ended " << std::endl;
 }

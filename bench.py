@@ -250,7 +250,34 @@ def main():
         line["e2e"] = {"value": cells * Ke / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 6 * 9 * cells * 8 / Ke,
                        "d2h_bytes_per_step": NF * cells * 8, "steps": Ke, "what": E2E_WHAT,
                        "passes_ms_per_step": [round(x / Ke * 1e3, 3) for x in dts]}
-        del f_host, g_host, out_host
+        # alternate output path (plbm_frames_begin): the visualiser's 12 CV_32F matrices + 19x9 series are
+        # formed on the device, 48 B per cell cross PCIe instead of 120.  Reported beside the headline, never as it.
+        fr_host = [torch.empty((12, nx, nx), dtype=torch.float32).pin_memory() for _ in range(2)]
+        se_host = [torch.empty((19, 9), dtype=torch.float64).pin_memory() for _ in range(2)]
+        fpt = C.POINTER(C.c_float)
+        frs = [(fpt * 12)(*[C.cast(h[k].data_ptr(), fpt) for k in range(12)]) for h in fr_host]
+        ses = [C.cast(h.data_ptr(), dp) for h in se_host]
+        lib.plbm_frames_begin.argtypes = [C.c_void_p, C.POINTER(fpt), dp]
+        dtf = []
+        for _rep in range(3):
+            sim.sync()
+            t0 = time.perf_counter()
+            if lib.plbm_upload_state(sim._h, fa, ga) != 0:
+                raise SystemExit(lib.plbm_last_error().decode())
+            for k in range(Ke):
+                if lib.plbm_step(sim._h, 1, 1) != 0 or lib.plbm_fetch_wait(sim._h) != 0 or lib.plbm_frames_begin(sim._h, frs[k & 1], ses[k & 1]) != 0:
+                    raise SystemExit(lib.plbm_last_error().decode())
+            if lib.plbm_fetch_wait(sim._h) != 0:
+                raise SystemExit(lib.plbm_last_error().decode())
+            sim.sync()
+            dtf.append(time.perf_counter() - t0)
+        line["e2e_frames"] = {"value": cells * Ke / min(dtf) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 6 * 9 * cells * 8 / Ke,
+                              "d2h_bytes_per_step": 12 * cells * 4 + 19 * 9 * 8, "steps": Ke,
+                              "what": "same loop through the alternate output path (LBmethod::Run_simulation_frames): per step the 12 float32 matrices "
+                                      "and 19x9 sample values the visualiser derives from the fields, formed on the device (bit-identical to the "
+                                      "visualiser's own narrowing); needs visualize::UpdateVisualizationFrames, so it is NOT the drop-in headline",
+                              "passes_ms_per_step": [round(x / Ke * 1e3, 3) for x in dtf]}
+        del f_host, g_host, out_host, fr_host, se_host
 
     # ---- cpu baseline (bounded sample of the same workload) -------------------------------
     if not args.no_cpu:

@@ -38,6 +38,9 @@ public:
     // The complete time loop of the reference (src/plasma.cpp:459-529): per step advance the
     // lattice on the device, copy the 15 visualised fields to the host, call the visualiser.
     void Run_simulation();
+    // same loop through the alternate output path: the visualiser's CV_32F matrices and sample-point series are
+    // formed on the device and handed to visualize::UpdateVisualizationFrames (include/visualize_frames.hpp)
+    void Run_simulation_frames();
 
     // ---- additions (not in the reference) used by benchmarks and tests -----------------------
     void Step(int nsteps, bool fetch_fields);                 // nsteps of the loop body without visualisation

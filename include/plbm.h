@@ -100,6 +100,20 @@ int plbm_download_fields(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
  * may be pending. */
 int plbm_fetch_begin(plbm_ctx* ctx, double* const out[PLBM_NUM_FIELDS]);
 int plbm_fetch_wait(plbm_ctx* ctx);
+/* Alternate output path.  visualize::UpdateVisualization narrows 12 quantities to CV_32F matrices
+ * (reference src/visualize.cpp:226-315: rho_e, rho_i, rho_q, ux_e, uy_e, |u_e|, ux_i, uy_i, |u_i|, T_e, T_i, T_n, each
+ * mat(y, x) = float(field[x + NX*y])) and records 19 series at 9 sample points (:168-219: ux, uy, |u| of e, i, n; T of
+ * e, i, n; rho of e, i, n; rho_q, Ex, Ey, |E|).  plbm_frames_begin forms exactly these on the device after a
+ * plbm_step(..., want_fields = 1) and starts copying them: 48 B per cell instead of 120 cross PCIe, bit-identical
+ * to what the unchanged visualiser would have built from the FP64 fields.  frames[k] = NX*NY_local floats (NULL:
+ * skip), series = [19][9] doubles (NULL: skip; on a slab, points outside it are left untouched).  Complete it with
+ * plbm_fetch_wait; the same one-pending rule as plbm_fetch_begin applies, and the next plbm_step may be issued
+ * at once.  A visualiser consumes them through visualize::UpdateVisualizationFrames (include/visualize_frames.hpp). */
+#define PLBM_NUM_FRAMES 12
+#define PLBM_NUM_SERIES 19
+#define PLBM_NUM_POINTS 9
+int plbm_frames_begin(plbm_ctx* ctx, float* const frames[PLBM_NUM_FRAMES], double* series);
+
 /* Page-lock / release a host range owned by the caller (cudaHostRegister) so that plbm_fetch_begin, plbm_upload_state
  * and plbm_download_* move it at full PCIe rate and asynchronously.  Optional: unpinned memory stays correct. */
 int plbm_pin_host(void* p, size_t bytes);

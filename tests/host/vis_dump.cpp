@@ -2,6 +2,7 @@
 // visualize:: entry points LBmethod::Run_simulation calls, writing the fields they receive as
 // raw float64 (order of the parameter list) for the steps listed in $PLBM_DUMP_STEPS.
 #include "visualize.hpp"
+#include "visualize_frames.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +37,21 @@ void UpdateVisualization(const int t, const int NX, const int NY,
     if (!fp) throw std::runtime_error(std::string("cannot open ") + name);
     const std::vector<double>* all[15] = { &ux_e, &uy_e, &ux_i, &uy_i, &ux_n, &uy_n, &T_e, &T_i, &T_n, &rho_e, &rho_i, &rho_n, &rho_q, &Ex, &Ey };
     for (auto* f : all) std::fwrite(f->data(), sizeof(double), static_cast<size_t>(NX) * NY, fp);
+    std::fclose(fp);
+}
+
+// alternate entry: the 12 CV_32F matrices as raw float32, then the 19 x 9 series as float64
+void UpdateVisualizationFrames(int t, int NX, int NY, const float* const mats[VF_COUNT], const double series[VS_COUNT][9])
+{
+    static const std::set<int> want = steps();
+    const char* dir = std::getenv("PLBM_DUMP_DIR");
+    if (!dir || !want.count(t)) return;
+    char name[512];
+    std::snprintf(name, sizeof(name), "%s/frames_t%05d.bin", dir, t);
+    FILE* fp = std::fopen(name, "wb");
+    if (!fp) throw std::runtime_error(std::string("cannot open ") + name);
+    for (int k = 0; k < VF_COUNT; ++k) std::fwrite(mats[k], sizeof(float), static_cast<size_t>(NX) * NY, fp);
+    std::fwrite(series, sizeof(double), static_cast<size_t>(VS_COUNT) * 9, fp);
     std::fclose(fp);
 }
 }

@@ -69,6 +69,49 @@ def test_lbmethod_run_simulation(oracle, plbm, NX, NY, steps, poisson, bc):
             assert_same_bits(got[t][n], want[t][n], f"LBmethod {NX}x{NY}/{poisson}/{bc} step {t}: {n}")
 
 
+def expected_frames_and_series(f: dict, NX: int, NY: int):
+    """What reference src/visualize.cpp:168-315 derives from the FP64 fields before its first OpenCV call."""
+    mag = lambda a, b: np.sqrt(a * a + b * b)                       # double, as in the reference
+    frames = [f["rho_e"], f["rho_i"], f["rho_q"], f["ux_e"], f["uy_e"], mag(f["ux_e"], f["uy_e"]),
+              f["ux_i"], f["uy_i"], mag(f["ux_i"], f["uy_i"]), f["T_e"], f["T_i"], f["T_n"]]
+    frames = np.stack([a.astype(np.float32) for a in frames])
+    cx, cy, dx, dy = NX // 2, NY // 2, NX // 4, NY // 4
+    pts = [(cx, cy), (cx + dx, cy), (cx - dx, cy), (cx, cy + dy), (cx, cy - dy),
+           (cx + dx, cy + dy), (cx + dx, cy - dy), (cx - dx, cy + dy), (cx - dx, cy - dy)]
+    at = lambda a: np.array([a[j, i] for i, j in pts])
+    rows = []
+    for sp in "ein":
+        rows += [at(f[f"ux_{sp}"]), at(f[f"uy_{sp}"]), at(mag(f[f"ux_{sp}"], f[f"uy_{sp}"]))]
+    rows += [at(f[f"T_{sp}"]) for sp in "ein"] + [at(f[f"rho_{sp}"]) for sp in "ein"]
+    rows += [at(f["rho_q"]), at(f["Ex"]), at(f["Ey"]), at(mag(f["Ex"], f["Ey"]))]
+    return frames, np.stack(rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NX,NY,steps,poisson,bc", [(64, 64, 12, "fft", "periodic"), (36, 28, 5, "sor", "bounceback")])
+def test_lbmethod_alternate_output_path(oracle, plbm, NX, NY, steps, poisson, bc):
+    """Run_simulation_frames: the visualiser's CV_32F matrices and sample series formed on the device are, bit for
+    bit, what the unchanged visualiser would have derived from the FP64 fields."""
+    build_drivers() if not (BUILD / "drive_lbmethod").exists() else None
+    dumps = sorted({0, 1, steps - 1})
+    with tempfile.TemporaryDirectory(prefix="plbm_frames_") as tmp:
+        env = dict(os.environ, PLBM_DUMP_DIR=tmp, PLBM_DUMP_STEPS=",".join(map(str, dumps)))
+        r = subprocess.run([str(BUILD / "drive_lbmethod"), str(NX), str(NY), str(steps), str(oracle.POISSON[poisson]), str(oracle.BC[bc]), "1"],
+                           capture_output=True, text=True, env=env, cwd=tmp)
+        assert r.returncode == 0, r.stderr
+        got = {}
+        for t in dumps:
+            raw = np.fromfile(os.path.join(tmp, f"frames_t{t:05d}.bin"), dtype=np.uint8)
+            nf = 12 * NX * NY * 4
+            got[t] = (raw[:nf].view(np.float32).reshape(12, NY, NX), raw[nf:].view(np.float64).reshape(19, 9))
+    o = oracle.PortOracle(NX, NY, poisson=poisson, bc=bc)
+    want = o.run_with_dumps(steps, dumps)
+    for t in dumps:
+        frames, series = expected_frames_and_series(want[t], NX, NY)
+        assert got[t][0].tobytes() == frames.tobytes() or np.array_equal(got[t][0], frames), f"frames differ at step {t}"
+        assert_same_bits(got[t][1], series, f"series at step {t}")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("NX,NY,steps,poisson,bc", [(40, 40, 6, "fft", "periodic"), (24, 36, 4, "none", "periodic"),
                                                      (22, 22, 4, "gs", "bounceback"), (24, 20, 4, "sor", "periodic")])
