@@ -60,30 +60,52 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs.
+
+    nvidia-smi needs 0.1-0.3 s before its first line, as long as the whole timed region of a default run, so the
+    sampling loop is started BEFORE the warm-up (start()); the `with` block only marks the timed window, and the
+    summary is taken from the lines that arrived inside it (each line is stamped on arrival; one sampling period
+    of slack on either side, and if the window was shorter than that, the nearest line)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 20
 
     def __init__(self, index: int = 0):
         self.index = index
-        self.samples = []
+        self.samples = []               # (arrival time, line)
         self.proc = None
+        self.t_begin = self.t_end = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", str(self.PERIOD_MS)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
+    def wait_first(self, timeout: float = 3.0):
+        """Block until the sampling loop delivers lines (called after the warm-up, before the timed region)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.proc is None:
+            self.start()
+        self.wait_first()
+        self.t_begin = time.perf_counter()
+        return self
+
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
     def __exit__(self, *exc):
+        self.t_end = time.perf_counter()
+        time.sleep(1.5 * self.PERIOD_MS / 1e3)          # let the line that covers the end of the window arrive
         if self.proc:
             self.proc.terminate()
             try:
@@ -92,9 +114,15 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
+        slack = self.PERIOD_MS / 1e3
+        lo, hi = (self.t_begin or 0.0) - slack, (self.t_end or float("inf")) + slack
+        inside = [ln for (ts, ln) in self.samples if lo <= ts <= hi]
+        if not inside and self.samples and self.t_begin is not None:
+            mid = 0.5 * (self.t_begin + self.t_end)
+            inside = [min(self.samples, key=lambda s: abs(s[0] - mid))[1]]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.samples:
+        for ln in inside:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -135,7 +163,9 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nx = args.nx or 2048
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    arm_nx = args.nx or (WEAK_SIDES.get(world, 2048) if world > 1 else 2048)      # the lattice the b200 arm runs at this N
+    nx = min(arm_nx, 2048)      # bounded sample: the reference keeps ~2.15 kB of host memory per cell (81 GB at 6144^2)
     threads = os.cpu_count() or 1
     steps = max(1, min(args.steps, args.cpu_steps * 3))
     warm = 1 if args.warmup > 0 else 0
@@ -145,11 +175,13 @@ def reference_arm(args):
     mlups, kind, info = run_cpu_reference(nx, steps, args.poisson, threads)
     wall = time.perf_counter() - t0
     sample = (f"{nx}x{nx} lattice, {steps} time steps of the unmodified reference loop (time loop only; constructor "
-              f"{info.get('ctor_s', 0):.1f}s excluded), FFTW replaced by oracle/fft_oracle.c, visualisation disabled")
+              f"{info.get('ctor_s', 0):.1f}s excluded), FFTW replaced by oracle/fft_oracle.c, visualisation disabled"
+              + ("" if nx == arm_nx else f"; bounded sample of the {arm_nx}x{arm_nx} workload (MLUPS is per cell update; the full lattice "
+                                         f"would need {arm_nx * arm_nx * 2150 / 1e9:.0f} GB of host memory in the reference's layout)"))
     line = {"impl": "reference", "metric": "MLUPS (all species)", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": info.get("loop_s", wall) / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{nx}x{nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic"},
+            "config": {"workload": f"{arm_nx}x{arm_nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic"},
             "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -181,6 +213,7 @@ def main():
         multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src)
         return
     nx = args.nx or 2048
+    sampler = ClockSampler(local_rank).start()          # running before the warm-up, see ClockSampler
     sim = P.PlasmaLBM(nx, nx, poisson=args.poisson, device=local_rank)
     sim.step(W)
     sim.sync()
@@ -188,7 +221,7 @@ def main():
     ext = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local_rank))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t = {"ms_k1": 0.0, "ms_poisson": 0.0, "launches": 0}
-    with ClockSampler(local_rank) as clocks:
+    with sampler as clocks:
         with torch.cuda.stream(ext):
             ev0.record()
         for n in segments(K):
@@ -351,13 +384,14 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
     """Slab decomposition over `world` GPUs: halo send/recv + two all-to-alls per step (NCCL)."""
     import torch.distributed as dist
     nx = args.nx or WEAK_SIDES.get(world) or (int(2048 * world ** 0.5) // 64 * 64)
+    sampler = ClockSampler(local_rank).start()
     b = P.CudaSlabBackend(nx, nx, rank, world, poisson=args.poisson, device=local_rank)
     drv = P.SlabDriver(b)
     drv.step(min(W, SEGMENT))
     b.sync(); torch.cuda.synchronize(); dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k1_events = []
-    with ClockSampler(local_rank) as clocks:
+    with sampler as clocks:
         with b.stream_context():
             ev0.record()
         for n in segments(K):
@@ -383,7 +417,7 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
                   if drv.peer else "2 all-to-all transposes of the half spectrum (NCCL)")
     line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + {transposes} + 1 phi row per side"
     line["clocks"] = clocks.summary()
-    line["gpu_launches"] = K * 8
+    line["gpu_launches"] = K * (9 if drv.peer else 6)      # K1, halo pack/push, P1, P2, P3, unpack (+ 3 barrier kernels with peer memory)
     if not args.no_e2e:
         import ctypes as C
         Ke = max(1, min(args.e2e_steps, K))
