@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "lbm_consts.h"
+#include "walls.cuh"
 
 namespace plbm {
 
@@ -21,5 +22,9 @@ cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, co
 // below/above: boundary rows of phi owned by the neighbouring slabs, nullptr on a single slab
 cudaError_t launch_k1_fused_phi(const double* src, double* dst, const double* phi, const double* below, const double* above, double* rho_q,
                                 const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
+
+// bounce-back walls (single slab): the pull follows walls.cuh, E comes from the arrays
+cudaError_t launch_k1_fused_walls(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,
+                                  const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, const WallArgs& wa, cudaStream_t stream);
 
 } // namespace plbm

@@ -1,5 +1,6 @@
 // layout.cu -- K4 (AoS <-> SoA) and the initial condition.  See layout.h.
 #include "layout.h"
+#include "walls.cuh"
 
 namespace plbm {
 
@@ -38,9 +39,58 @@ __global__ void soa_to_aos_kernel(const double* __restrict__ planes, double* __r
     }
 }
 
+// walls: the planes hold the state at the top of the loop itself (identity) ...
+__global__ void aos_to_soa_identity_kernel(const double* __restrict__ aos, double* __restrict__ planes, int sk, LbmGeom g)
+{
+    const long long n = (long long)g.NX * g.NYl * NQ;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % NQ);
+        const long long c = t / NQ;
+        const int x = (int)(c % g.NX), y = (int)(c / g.NX);
+        planes[(long long)(sk * NQ + i) * g.plane + (long long)(y + 1) * g.pitch + x] = aos[t];
+    }
+}
+// ... or post-collision values that still have to be streamed against the walls (walls.cuh): sk = species*2 + kind
+__global__ void soa_to_aos_walls_kernel(const double* __restrict__ planes, const double* __restrict__ rim, int nrim,
+                                        double* __restrict__ aos, int sk, LbmGeom g, int identity)
+{
+    const long long n = (long long)g.NX * g.NYl * NQ;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(t % NQ);
+        const long long c = t / NQ;
+        const int x = (int)(c % g.NX), y = (int)(c / g.NX);
+        const long long own = (long long)(y + 1) * g.pitch + x;
+        double v;
+        if (identity) v = planes[(long long)(sk * NQ + j) * g.plane + own];
+        else {
+            const WallSource ws = wall_source(x, y, j, g.NX, g.NYl);
+            if (ws.dir >= 0) v = planes[(long long)(sk * NQ + ws.dir) * g.plane + (long long)(ws.y + 1) * g.pitch + ws.x];
+            else if (sk & 1) v = planes[(long long)((sk - 1) * NQ + j) * g.plane + own];                      // g: post-collision f
+            else v = rim[((long long)((sk >> 1) * NQ + j)) * nrim + wall_rim_index(x, y, g.NX, g.NYl)];       // f: its pre-collision value
+        }
+        aos[t] = v;
+    }
+}
+
 struct InitParams {
     double rho_init[3], T_init[3], w[3];
 };
+
+// LBmethod::Initialize (plasma.cpp:131-158) at the cells themselves (walls: the first step does not stream)
+__global__ void initialize_identity_kernel(double* __restrict__ planes, LbmGeom g, int NY, InitParams p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= g.NX || y >= g.NYl) return;
+    const bool inside = (x >= g.NX / 4 + 1) && (x < 3 * g.NX / 4) && (y >= NY / 4 + 1) && (y < 3 * NY / 4);
+    const long long own = (long long)(y + 1) * g.pitch + x;
+    for (int s = 0; s < 3; ++s)
+        for (int i = 0; i < NQ; ++i) {
+            const double w = p.w[i == 0 ? 0 : (i < 5 ? 1 : 2)];
+            const bool on = (s == 2) || inside;
+            planes[(long long)((s * 2 + 0) * NQ + i) * g.plane + own] = on ? __dmul_rn(w, p.rho_init[s]) : 0.0;
+            planes[(long long)((s * 2 + 1) * NQ + i) * g.plane + own] = on ? __dmul_rn(w, p.T_init[s]) : 0.0;
+        }
+}
 
 // plane value at storage position (xs, row rr) of direction i = initial f_i at the cell that
 // pulls from there, i.e. (xs + cx_i, ys + cy_i) with periodic wrap on the GLOBAL lattice.
@@ -115,6 +165,26 @@ cudaError_t launch_aos_to_soa(const double* aos, double* planes, int species, in
 cudaError_t launch_soa_to_aos(const double* planes, double* aos, int species, int kind, const LbmGeom& g, cudaStream_t s)
 {
     soa_to_aos_kernel<<<grid_for((long long)g.NX * g.NYl * NQ, 256), 256, 0, s>>>(planes, aos, species * 2 + kind, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_initialize_identity(double* planes, const LbmGeom& g, int NY,
+                                       const double rho_init[3], const double T_init[3], const double w[3], cudaStream_t s)
+{
+    InitParams p;
+    for (int k = 0; k < 3; ++k) { p.rho_init[k] = rho_init[k]; p.T_init[k] = T_init[k]; p.w[k] = w[k]; }
+    dim3 grid((g.NX + 127) / 128, g.NYl);
+    initialize_identity_kernel<<<grid, 128, 0, s>>>(planes, g, NY, p);
+    return cudaGetLastError();
+}
+cudaError_t launch_aos_to_soa_identity(const double* aos, double* planes, int species, int kind, const LbmGeom& g, cudaStream_t s)
+{
+    aos_to_soa_identity_kernel<<<grid_for((long long)g.NX * g.NYl * NQ, 256), 256, 0, s>>>(aos, planes, species * 2 + kind, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_soa_to_aos_walls(const double* planes, const double* rim, int nrim, double* aos, int species, int kind,
+                                    const LbmGeom& g, int identity, cudaStream_t s)
+{
+    soa_to_aos_walls_kernel<<<grid_for((long long)g.NX * g.NYl * NQ, 256), 256, 0, s>>>(planes, rim, nrim, aos, species * 2 + kind, g, identity);
     return cudaGetLastError();
 }
 cudaError_t launch_initialize(double* planes, const LbmGeom& g, int NY, int y0,

@@ -20,7 +20,7 @@ struct LitMacro {
 };
 
 // f, g: [species][direction] populations at the top of the time loop (already streamed)
-__device__ __noinline__ void lit_update_macro(const D (&f)[3][9], const D (&g)[3][9], D Ex, D Ey, const LbmConsts& c, LitMacro& m)
+static __device__ __noinline__ void lit_update_macro(const D (&f)[3][9], const D (&g)[3][9], D Ex, D Ey, const LbmConsts& c, LitMacro& m)
 {
     const int cx[9] = { 0, 1, 0, -1, 0, 1, -1, -1, 1 }, cy[9] = { 0, 0, 1, 0, -1, 1, 1, -1, -1 };
     D rl[3];
@@ -73,7 +73,7 @@ __device__ __forceinline__ D lit_thermal_term(D rho, D tau, D feq)             /
 }
 
 // direction i of all three species: fi/gi in, post-collision values out
-__device__ __noinline__ void lit_collide_direction(int i, const D (&fi)[3], const D (&gi)[3], const LitMacro& m, D Ex, D Ey,
+static __device__ __noinline__ void lit_collide_direction(int i, const D (&fi)[3], const D (&gi)[3], const LitMacro& m, D Ex, D Ey,
                                                    const LbmConsts& c, D (&fo)[3], D (&go)[3])
 {
     const int cxs[9] = { 0, 1, 0, -1, 0, 1, -1, -1, 1 }, cys[9] = { 0, 0, 1, 0, -1, 1, 1, -1, -1 };

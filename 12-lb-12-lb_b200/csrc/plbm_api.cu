@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -149,6 +150,11 @@ struct plbm_ctx {
     int slab_k0[PLBM_MAX_RANKS + 1] = {};
     // unfused device path (bounce-back walls): the reference's own array set in its own layout
     bool unfused = false;
+    // fused walls path (default for bounce-back): K1 with the walls pull (walls.cuh)
+    bool walls = false;
+    double* rim[2] = { nullptr, nullptr };   // pre-collision f of the wall cells, ping-pong
+    int rim_cur = 0;
+    bool identity_pull = true;               // pop[cur] is the state at the top of the loop itself
     PhaseArrays pa = {};
     PhaseUnits pu = {};
     std::vector<double*> uf_bufs;
@@ -372,7 +378,13 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
         mo.ux[s] = c->macro[2 * s]; mo.uy[s] = c->macro[2 * s + 1];
         mo.T[s] = c->macro[6 + s]; mo.rho[s] = c->macro[9 + s];
     }
-    if (c->e_stale) {
+    if (c->walls) {
+        const WallArgs wa = { c->rim[c->rim_cur], c->rim[c->rim_cur ^ 1], wall_rim_count(c->cfg.NX, c->geom.NYl), c->identity_pull ? 1 : 0 };
+        CUDA_TRY(launch_k1_fused_walls(c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->rho_q, want_fields ? &mo : nullptr,
+                                       c->consts, c->geom, wa, c->stream));
+        c->rim_cur ^= 1;
+        c->identity_pull = false;
+    } else if (c->e_stale) {
         const bool slabs = c->cfg.nranks > 1;
         CUDA_TRY(launch_k1_fused_phi(c->pop[c->cur], c->pop[c->cur ^ 1], c->phi, slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr,
                                      c->rho_q, want_fields ? &mo : nullptr, c->consts, c->geom, c->stream));
@@ -459,7 +471,13 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     CUDA_OR_DESTROY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)cfg->NX * c->geom.NYl;
     const size_t pop_count = (size_t)NPLANES * c->geom.plane;
-    c->unfused = (cfg->bc_type == PLBM_BC_BOUNCEBACK) && !cfg->fields_only;
+    {
+        const char* e = std::getenv("PLBM_UNFUSED_WALLS");       // the reference's own sweep sequence instead of the fused kernel
+        const bool want_unfused = e && e[0] && e[0] != '0';
+        const bool bb = (cfg->bc_type == PLBM_BC_BOUNCEBACK) && !cfg->fields_only;
+        c->unfused = bb && want_unfused;
+        c->walls = bb && !want_unfused;
+    }
     for (int b = 0; b < 2 && !cfg->fields_only && !c->unfused; ++b) {
         TRY_OR_DESTROY(dev_alloc(c, &c->pop[b], pop_count));
         CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
@@ -473,6 +491,13 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
         c->macro[k] = c->macro_sets[0][k];
     }
     if (!cfg->fields_only && !c->unfused) TRY_OR_DESTROY(dev_alloc(c, &c->staging, n * NQ));
+    if (c->walls) {
+        const size_t nr = (size_t)3 * NQ * wall_rim_count(cfg->NX, c->geom.NYl);
+        for (int b = 0; b < 2; ++b) {
+            TRY_OR_DESTROY(dev_alloc(c, &c->rim[b], nr));
+            CUDA_OR_DESTROY(cudaMemsetAsync(c->rim[b], 0, sizeof(double) * nr, c->stream));
+        }
+    }
     TRY_OR_DESTROY(dev_alloc(c, &c->err_bits, 2));
     TRY_OR_DESTROY(dev_alloc(c, &c->iters_dev, 1));
     if (c->unfused) {
@@ -524,6 +549,7 @@ void plbm_destroy(plbm_ctx* c)
     for (int b = 0; b < 2; ++b) for (int k = 0; k < 12; ++k) cudaFree(c->macro_sets[b][k]);
     for (int k = 0; k < 4; ++k) cudaFree(c->snap[k]);
     cudaFree(c->frames); cudaFree(c->series);
+    cudaFree(c->rim[0]); cudaFree(c->rim[1]);
     if (c->ev_snap) cudaEventDestroy(c->ev_snap);
     if (c->ev_fetched) cudaEventDestroy(c->ev_fetched);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -559,6 +585,10 @@ int plbm_initialize(plbm_ctx* c)
     // the state of a freshly constructed LBmethod (reference src/plasma.cpp:58-124): initial populations,
     // E = E_ext, phi = 0 and the Poisson module's call_once not yet taken
     const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
+    if (c->walls) {
+        CUDA_TRY(launch_initialize_identity(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
+        c->identity_pull = true;
+    } else
     CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
     CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
     CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
@@ -590,8 +620,10 @@ int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const
             const double* h = kind ? g[s] : f[s];
             if (!h) return fail("plbm_upload_state: null array (species %d)", s);
             CUDA_TRY(cudaMemcpyAsync(c->staging, h, bytes, cudaMemcpyHostToDevice, c->stream));
-            CUDA_TRY(launch_aos_to_soa(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+            if (c->walls) CUDA_TRY(launch_aos_to_soa_identity(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+            else CUDA_TRY(launch_aos_to_soa(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
         }
+    if (c->walls) c->identity_pull = true;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -614,7 +646,10 @@ int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
         for (int kind = 0; kind < 2; ++kind) {
             double* h = kind ? g[s] : f[s];
             if (!h) continue;
-            CUDA_TRY(launch_soa_to_aos(c->pop[c->cur], c->staging, s, kind, c->geom, c->stream));
+            if (c->walls)
+                CUDA_TRY(launch_soa_to_aos_walls(c->pop[c->cur], c->rim[c->rim_cur], wall_rim_count(c->cfg.NX, c->geom.NYl), c->staging, s, kind,
+                                                 c->geom, c->identity_pull ? 1 : 0, c->stream));
+            else CUDA_TRY(launch_soa_to_aos(c->pop[c->cur], c->staging, s, kind, c->geom, c->stream));
             CUDA_TRY(cudaMemcpyAsync(h, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
         }

@@ -208,3 +208,11 @@ def test_pipelined_fetch_delivers_every_step(oracle, plbm, poisson, bc):
             sim.fetch_begin(bufs[1])                     # a second fetch before fetch_wait is refused
         sim.fetch_wait()
     o.close()
+
+
+@pytest.mark.parametrize("poisson", ["none", "sor"])
+def test_walls_through_the_unfused_sweep_sequence(oracle, plbm, monkeypatch, poisson):
+    """PLBM_UNFUSED_WALLS=1 keeps the first wall implementation reachable: the reference's own sequence of sweeps on
+    its own array set (the default is the fused kernel with the walls pull, csrc/walls.cuh)."""
+    monkeypatch.setenv("PLBM_UNFUSED_WALLS", "1")
+    run_both(oracle, plbm, 30, 26, poisson, 6, {0, 1, 5}, bc="bounceback")
