@@ -667,14 +667,50 @@ int plbm_set_efield(plbm_ctx* c, const double* Ex, const double* Ey)
     return 0;
 }
 
+// Small lattices are launch-bound (at 200 x 200 every kernel is less than one wave and a step is four launches): long
+// runs of steps are replayed from a CUDA graph of TWO steps (two, so that the ping-pong buffers are back where they were).
+// The first two steps run eagerly -- they settle everything a later step does not repeat (call_once of the Poisson module,
+// field source, kernel attributes) -- and so does the tail, including the step whose moments are asked for.
+constexpr long long GRAPH_MAX_CELLS = 1 << 20;
+constexpr int GRAPH_MIN_STEPS = 24;
+
 int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
 {
     if (!c) return fail("plbm_step: null context");
     if (c->cfg.nranks > 1) return fail("plbm_step: this context is one slab of %d; drive it with plbm_step_local / plbm_halo_* / plbm_poisson_stage", c->cfg.nranks);
-    for (int t = 0; t < nsteps; ++t) {
-        if (one_step(c, want_fields && t == nsteps - 1, nullptr)) return 1;
-        if (solve_poisson_in_loop(c, nullptr)) return 1;
+    auto eager = [&](int from, int to) -> int {
+        for (int t = from; t < to; ++t) {
+            if (one_step(c, want_fields && t == nsteps - 1, nullptr)) return 1;
+            if (solve_poisson_in_loop(c, nullptr)) return 1;
+        }
+        return 0;
+    };
+    static const bool graphs_off = []() { const char* e = std::getenv("PLBM_NO_GRAPH"); return e && e[0] && e[0] != '0'; }();
+    const long long cells = (long long)c->cfg.NX * c->geom.NYl;
+    int done = 0;
+    if (!graphs_off && !c->unfused && c->pop[0] && cells <= GRAPH_MAX_CELLS && nsteps >= GRAPH_MIN_STEPS) {
+        if (eager(0, 2)) return 1;
+        done = 2;
+        const int pairs = (nsteps - 1 - done) / 2;              // the last step stays eager (it may have to write the moments)
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = eager(done, done + 2) ;                  // recorded, not run; host-side state advances as if it had run
+        const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc ? 1 : fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        }
+        CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+        for (int k = 0; k < pairs; ++k) CUDA_TRY(cudaGraphLaunch(exec, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));            // the executable graph must outlive its launches
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        done += 2 * pairs;
+        // host-side ping-pong state: the recorded pair advanced it once; the replays are whole pairs and leave it unchanged
+        if (pairs == 0) return fail("plbm_step: internal: empty graph replay");
     }
+    if (eager(done, nsteps)) return 1;
     if (want_fields && materialise_efield(c)) return 1;
     return 0;
 }

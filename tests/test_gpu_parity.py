@@ -216,3 +216,26 @@ def test_walls_through_the_unfused_sweep_sequence(oracle, plbm, monkeypatch, poi
     its own array set (the default is the fused kernel with the walls pull, csrc/walls.cuh)."""
     monkeypatch.setenv("PLBM_UNFUSED_WALLS", "1")
     run_both(oracle, plbm, 30, 26, poisson, 6, {0, 1, 5}, bc="bounceback")
+
+
+@pytest.mark.parametrize("poisson,bc,nsteps", [("fft", "periodic", 41), ("none", "periodic", 30), ("sor", "bounceback", 26), ("none", "bounceback", 33)])
+def test_long_runs_replayed_from_a_cuda_graph(oracle, plbm, poisson, bc, nsteps):
+    """plbm_step with many steps on a small lattice records two steps into a CUDA graph and replays it; the result must be
+    the one of step-by-step execution (odd and even step counts, moments of the last step included)."""
+    NX, NY = 40, 36
+    o = oracle.PortOracle(NX, NY, poisson=poisson, bc=bc)
+    o.step(nsteps)
+    with plbm.PlasmaLBM(NX, NY, poisson=poisson, bc=bc) as sim:
+        sim.step(nsteps, want_fields=True)
+        assert_fields_same(sim.fields(), o.fields(), f"graph replay {poisson}/{bc}/{nsteps}")
+        f, g = sim.download_state()
+        sim.step(nsteps + 1)                         # a second long call on the same context
+        f2, g2 = sim.download_state()
+    for s in range(3):
+        assert_same_bits(f[s], o.f(s), f"graph replay: f[{s}]")
+        assert_same_bits(g[s], o.g(s), f"graph replay: g[{s}]")
+    o.step(nsteps + 1)
+    for s in range(3):
+        assert_same_bits(f2[s], o.f(s), f"graph replay, second call: f[{s}]")
+        assert_same_bits(g2[s], o.g(s), f"graph replay, second call: g[{s}]")
+    o.close()
