@@ -9,9 +9,9 @@
 // the previous step's phi, and stop after the FIRST iteration whose largest update is below 1e-8
 // (or after 5000 iterations).  Cells of one colour are independent, so a colour sweep is
 // order-independent and bit-reproducible; to stop at exactly the reference's iteration without a
-// host round trip per iteration, the whole solve is ONE cooperative kernel: grid-wide barriers
-// between colour sweeps, the iteration's maximum update reduced with warp shuffles and one
-// atomicMax per warp on the (non-negative) double's bit pattern.
+// host round trip per iteration, the whole solve is ONE cooperative kernel: one grid-wide barrier
+// per colour sweep, the iteration's maximum update reduced with warp shuffles and one atomicMax
+// per warp on the (non-negative) double's bit pattern before the last colour's barrier.
 #include "poisson_iter.h"
 
 #include <cooperative_groups.h>
@@ -66,12 +66,14 @@ poisson_iter_kernel(double* phi, const double* __restrict__ rho_q, int NX, int N
                 phi[c] = nw;
                 local = fmax(local, fabs(__dsub_rn(nw, old)));
             }
-            grid.sync();                                       // the next colour reads this colour's updates
+            if (colour == NCOL - 1) {                          // the barrier that ends the last colour also completes the reduction
+                local = warp_max(local);
+                if ((threadIdx.x & 31) == 0) atomicMax(slot, (unsigned long long)__double_as_longlong(local));
+            }
+            grid.sync();                                       // the next colour (or iteration) reads this colour's updates
+            // the other slot was last read after the previous iteration's final barrier: every thread is past that now
+            if (colour == 0 && tid == 0) err_bits[(iter + 1) & 1] = 0ull;
         }
-        local = warp_max(local);
-        if ((threadIdx.x & 31) == 0) atomicMax(slot, (unsigned long long)__double_as_longlong(local));
-        if (tid == 0) err_bits[(iter + 1) & 1] = 0ull;         // clear the other slot for the next iteration
-        grid.sync();
         const double maxErr = __longlong_as_double((long long)*(volatile unsigned long long*)slot);
         if (maxErr < ITER_TOL) { ++iter; break; }              // poisson.cpp:137-140, 275-277, 479-481
     }
