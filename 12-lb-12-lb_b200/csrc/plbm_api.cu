@@ -588,8 +588,9 @@ int plbm_initialize(plbm_ctx* c)
     if (c->walls) {
         CUDA_TRY(launch_initialize_identity(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
         c->identity_pull = true;
-    } else
-    CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
+    } else {
+        CUDA_TRY(launch_initialize(c->pop[c->cur], c->geom, c->cfg.NY, c->cfg.y0, c->cfg.rho_init, c->cfg.T_init, c->consts.w, c->stream));
+    }
     CUDA_TRY(launch_fill(c->Ex, c->cfg.Ex_ext, n, c->stream));
     CUDA_TRY(launch_fill(c->Ey, c->cfg.Ey_ext, n, c->stream));
     c->e_stale = false;
@@ -620,8 +621,11 @@ int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const
             const double* h = kind ? g[s] : f[s];
             if (!h) return fail("plbm_upload_state: null array (species %d)", s);
             CUDA_TRY(cudaMemcpyAsync(c->staging, h, bytes, cudaMemcpyHostToDevice, c->stream));
-            if (c->walls) CUDA_TRY(launch_aos_to_soa_identity(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
-            else CUDA_TRY(launch_aos_to_soa(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+            if (c->walls) {
+                CUDA_TRY(launch_aos_to_soa_identity(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+            } else {
+                CUDA_TRY(launch_aos_to_soa(c->staging, c->pop[c->cur], s, kind, c->geom, c->stream));
+            }
         }
     if (c->walls) c->identity_pull = true;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -646,10 +650,12 @@ int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
         for (int kind = 0; kind < 2; ++kind) {
             double* h = kind ? g[s] : f[s];
             if (!h) continue;
-            if (c->walls)
+            if (c->walls) {
                 CUDA_TRY(launch_soa_to_aos_walls(c->pop[c->cur], c->rim[c->rim_cur], wall_rim_count(c->cfg.NX, c->geom.NYl), c->staging, s, kind,
                                                  c->geom, c->identity_pull ? 1 : 0, c->stream));
-            else CUDA_TRY(launch_soa_to_aos(c->pop[c->cur], c->staging, s, kind, c->geom, c->stream));
+            } else {
+                CUDA_TRY(launch_soa_to_aos(c->pop[c->cur], c->staging, s, kind, c->geom, c->stream));
+            }
             CUDA_TRY(cudaMemcpyAsync(h, c->staging, bytes, cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
         }
