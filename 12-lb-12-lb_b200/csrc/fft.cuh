@@ -50,6 +50,7 @@ struct FftPlan {
     int n44;                        // leading FFT_PASS_44 passes
     int tail;                       // FftTail: the 4/2 pass after them
     int odd;                        // FftOdd
+    int n3;                         // FFT_ODD_35: number of radix-3 stages (they precede the radix-5 stages)
     int threads;                    // CTA size the passes need: ceil(n/16), or ceil(n/15) with radix-3/5 register passes
     FftPass pass[FFT_MAX_PASSES];
     const cpx* tw;                  // device: n forward twiddles exp(-2 pi i t / n)
@@ -268,8 +269,9 @@ __device__ __forceinline__ void fft_pass_small_odd(int n, const FftPass ps, cons
 // (4,2) / (4) / (2), then odd primes.  Keeping the pass bodies out of a runtime switch lets ptxas allocate each
 // body's 16 complex registers independently (a switch over the bodies made it spill).
 enum FftTail { FFT_TAIL_NONE = 0, FFT_TAIL_42 = 1, FFT_TAIL_4 = 2, FFT_TAIL_2 = 3 };
-// odd part of the schedule: none; 3 / 5 = every odd stage has that radix (register passes); generic otherwise
-enum FftOdd { FFT_ODD_NONE = 0, FFT_ODD_GENERIC = 1, FFT_ODD_3 = 3, FFT_ODD_5 = 5 };
+// odd part of the schedule: none; 3 / 5 = every odd stage has that radix, 15 = radix 3 and 5 mixed (register passes);
+// generic otherwise
+enum FftOdd { FFT_ODD_NONE = 0, FFT_ODD_GENERIC = 1, FFT_ODD_3 = 3, FFT_ODD_5 = 5, FFT_ODD_35 = 15 };   // 15: stages of radix 3 and 5 mixed
 
 // Transform of length P.n from `in` to `out` (element index -> value functors with load/store and a static
 // `is_smem`), through the padded shared buffer `buf`.  All threads of the CTA must call it.  If `in` reads shared
@@ -299,7 +301,22 @@ __device__ __forceinline__ void fft_run(const FftPlan& P, cpx* buf, const In& in
         else fft_pass_pow2<SIGN, 2, 1>(P.n, P.pass[i], P.tw, src, dst);
         ++i;
     }
-    if constexpr (ODD != FFT_ODD_NONE) {
+    if constexpr (ODD == FFT_ODD_35) {
+        // primes ascend in the schedule: all radix-3 stages, then all radix-5 stages -- two loops, one body each
+        const int end3 = i + P.n3;
+        #pragma unroll 1
+        for (; i < end3; ++i) {
+            const FftSource<In> src{ in, buf, i == 0 };
+            const FftSink<Out> dst{ out, buf, i == last };
+            fft_pass_small_odd<SIGN, 3>(P.n, P.pass[i], P.tw, src, dst);
+        }
+        #pragma unroll 1
+        for (; i < P.npass; ++i) {
+            const FftSource<In> src{ in, buf, i == 0 };
+            const FftSink<Out> dst{ out, buf, i == last };
+            fft_pass_small_odd<SIGN, 5>(P.n, P.pass[i], P.tw, src, dst);
+        }
+    } else if constexpr (ODD != FFT_ODD_NONE) {
         #pragma unroll 1
         for (; i < P.npass; ++i) {
             const FftSource<In> src{ in, buf, i == 0 };

@@ -57,14 +57,17 @@ FftPlan make_fft_plan(int n, const cpx* tw)
         else {
             ps.kind = FFT_PASS_ODD; R = radix[i]; ps.r = (unsigned short)R; i += 1;
             const int small = (R == 3 || R == 5) ? R : FFT_ODD_GENERIC;
-            P.odd = (P.odd == FFT_ODD_NONE || P.odd == small) ? small : FFT_ODD_GENERIC;
+            if (R == 3) P.n3++;
+            if (P.odd == FFT_ODD_NONE || P.odd == small) P.odd = small;
+            else if (small != FFT_ODD_GENERIC && (P.odd == FFT_ODD_3 || P.odd == FFT_ODD_5 || P.odd == FFT_ODD_35)) P.odd = FFT_ODD_35;
+            else P.odd = FFT_ODD_GENERIC;
         }
         nsub /= R;
         ps.m = nsub;
         s *= R;
         while ((1 << (log2s + 1)) <= s) ++log2s;
     }
-    const int per_thread = (P.odd == FFT_ODD_3 || P.odd == FFT_ODD_5) ? 15 : FFT_EPT;
+    const int per_thread = (P.odd == FFT_ODD_3 || P.odd == FFT_ODD_5 || P.odd == FFT_ODD_35) ? 15 : FFT_EPT;
     P.threads = ((n + per_thread - 1) / per_thread + 31) & ~31;
     if (P.threads < 64) P.threads = 64;
     if (P.threads > 512 && P.odd != FFT_ODD_NONE) {               // the 768-thread kernels carry the generic odd pass only

@@ -36,6 +36,7 @@ inline cudaError_t with_shape(const FftPlan& P, F&& f)
         switch (P.odd) {
         case FFT_ODD_3: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_3>{});
         case FFT_ODD_5: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_5>{});
+        case FFT_ODD_35: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_35>{});
         case FFT_ODD_GENERIC: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_GENERIC>{});
         default: return f(std::integral_constant<int, 512>{}, TAIL, std::integral_constant<int, FFT_ODD_NONE>{});
         }

@@ -1,6 +1,7 @@
 """The spectral Poisson solve on its own (poisson::SolvePoisson, FFT + periodic field) against the CPU checker,
 bit for bit, over the sequence lengths the pass scheduler treats differently: pure powers of four, 4..4,2 tails,
-single 4 / 2 passes, odd primes after the 4/2 passes, odd-only lengths, and the benchmark's sizes."""
+single 4 / 2 passes, odd primes after the 4/2 passes (radix 3, radix 5, both mixed, larger primes), odd-only lengths,
+and the benchmark's sizes."""
 import numpy as np
 import pytest
 
@@ -8,7 +9,8 @@ from helpers import assert_same_bits
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [3, 4, 5, 8, 16, 17, 25, 27, 32, 49, 64, 96, 100, 121, 128, 200, 243, 256, 384, 500, 512, 1000, 1024, 1536]
+SIZES = [3, 4, 5, 8, 15, 16, 17, 25, 27, 30, 32, 45, 49, 60, 64, 75, 96, 100, 121, 128, 200, 225, 243, 256, 360, 384, 500, 512, 720,
+         1000, 1024, 1536]
 
 
 def solve_both(oracle, plbm, NX, NY, seed):
@@ -43,6 +45,7 @@ def test_benchmark_sizes(oracle, plbm, n):
     solve_both(oracle, plbm, n, n, seed=n)
 
 
-@pytest.mark.parametrize("NX,NY", [(8192, 16), (16, 8192), (6144, 12), (12, 6144), (12288, 4), (4, 12288), (10007, 3)])
+@pytest.mark.parametrize("NX,NY", [(8192, 16), (16, 8192), (6144, 12), (12, 6144), (12288, 4), (4, 12288), (10007, 3),
+                                   (5760, 8), (8, 5760), (2880, 6), (7680, 4), (4, 7500)])
 def test_longest_sequences(oracle, plbm, NX, NY):
     solve_both(oracle, plbm, NX, NY, seed=NX + NY)
