@@ -25,3 +25,28 @@ def test_bench_csv_keeps_the_reference_columns(tmp_path):
     assert gpu[:5] == ["2048x2048", "192", "0", "3", "0"] and abs(float(gpu[5]) - 1.147 * 192) < 1e-6
     assert gpu[6] == "1" and float(gpu[7]) == 3656.5 and float(gpu[9]) == 0.548
     assert cpu[:5] == ["2048x2048", "12", "16", "3", "0"] and cpu[6] == "0"
+
+
+def test_bench_clock_sampler_windows_its_samples():
+    """bench.py's clock sampler keeps only the nvidia-smi lines that arrived inside the timed window (plus one period)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    s = bench.ClockSampler(0)
+    line = "1965, 1965, 612.3, Not Active, Not Active, Not Active, {}"
+    s.samples = [(9.90, line.format("Not Active")), (10.01, line.format("Active")), (10.05, line.format("Not Active")),
+                 (10.30, "1200, 1965, 100.0, Active, Not Active, Not Active, Not Active")]
+    s.t_begin, s.t_end = 10.0, 10.1
+    out = s.summary()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    s.t_begin, s.t_end = 20.0, 20.001                      # nothing inside: the nearest line is used
+    assert s.summary()["samples"] == 1
+    s.samples = []
+    assert s.summary() == {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+
+
+def test_bench_segments_cover_exactly_k_steps():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    for k in (1, 47, 48, 49, 192, 200):
+        seg = list(bench.segments(k))
+        assert sum(seg) == k and max(seg) <= bench.SEGMENT and min(seg) >= 1
