@@ -1,5 +1,6 @@
 // k1_fused.h -- launcher of the fused pull-stream + moments + equilibrium + collision kernel.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include "lbm_consts.h"
 #include "walls.cuh"
@@ -22,6 +23,16 @@ cudaError_t launch_k1_fused(const double* src, double* dst, const double* Ex, co
 // below/above: boundary rows of phi owned by the neighbouring slabs, nullptr on a single slab
 cudaError_t launch_k1_fused_phi(const double* src, double* dst, const double* phi, const double* below, const double* above, double* rho_q,
                                 const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
+
+// Periodic lattices, the pull done by the TMA engine (k1_kernel.cuh: k1_tma_kernel).  `tmap` describes the planes of `src` as
+// the 4-D tensor [6][9][NYl + 2][NX]; make_k1_tensor_map builds it (once per population buffer).  E comes from phi when
+// `phi` is given (below/above as in launch_k1_fused_phi), else from the Ex/Ey arrays.
+cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const LbmGeom& g);
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const double* src, double* dst, const double* Ex, const double* Ey,
+                          const double* phi, const double* below, const double* above, double* rho_q,
+                          const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
+int k1_tile_cells();      // cells per CTA (box extent in x)
+int k1_prefetch_rows(int NX, int NYl);   // LbmGeom::prefetch_rows for a slab of this shape on the current device
 
 // bounce-back walls (single slab): the pull follows walls.cuh, E comes from the arrays
 cudaError_t launch_k1_fused_walls(const double* src, double* dst, const double* Ex, const double* Ey, double* rho_q,

@@ -12,6 +12,9 @@ static cudaError_t k1_walls_launch(const double* src, double* dst, const double*
     if (!configured) {
         cudaError_t err = cudaFuncSetAttribute(k1_walls_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes());
         if (err != cudaSuccess) return err;
+        // the parked populations are the only on-chip data: give shared memory the carve-out the CTAs per SM need
+        if (PLBM_K1_CARVEOUT >= 0) err = cudaFuncSetAttribute(k1_walls_kernel<M>, cudaFuncAttributePreferredSharedMemoryCarveout, PLBM_K1_CARVEOUT);
+        if (err != cudaSuccess) return err;
         configured = true;
     }
     dim3 grid((g.NX + K1_THREADS - 1) / K1_THREADS, g.NYl);

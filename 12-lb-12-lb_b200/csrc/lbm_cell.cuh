@@ -136,6 +136,72 @@ __device__ __forceinline__ void cell_update_macro(DV& dv, const D (&rl)[3], cons
     m.rho_q = charge_density(dv, m.rho[0], m.rho[1], c);
 }
 
+// ---- the same UpdateMacro with the per-cell gate of exact_math.cuh (CellGate) instead of a record per division ------------
+// Noted here: raw densities (NaN detection), rho_s and T_s (upper bound; T_s also from below), the numerators mx, my of the
+// velocity divisions, the velocities ux_s, uy_s (both bounds), the pair densities and numerators, the pair velocities (upper
+// bound).  Divisions by the species' own density need no note: rho_s >= 1e-10 on that branch and rho_s < 2^200 is noted.
+template <int s>
+__device__ __forceinline__ void species_velocity(GatedDiv& dv, CellGate& gt, D rl, D mx, D my, D Ex, D Ey, const LbmConsts& c,
+                                                 D& rho, D& ux, D& uy)
+{
+    gt.note_raw_density(rl);
+    if (rl < D(1e-10)) {                                                      // plasma.cpp:373-377
+        rho = D(0.0); ux = D(0.0); uy = D(0.0);
+    } else {
+        rho = rl;
+        gt.note_scalar(rl);
+        gt.note_num(mx);
+        gt.note_num(my);
+        if constexpr (s < 2) {                                                // plasma.cpp:380-391, 400-411
+            D vx = dv.xdiv(mx, rl);
+            D vy = dv.xdiv(my, rl);
+            if (mx == rl || mx == -rl) vx = D(0.0);
+            if (my == rl || my == -rl) vy = D(0.0);
+            ux = vx + dv.cdiv(D(c.hq[s]) * Ex, c.m[s]);                        // 0.5*q*Ex/m
+            uy = vy + dv.cdiv(D(c.hq[s]) * Ey, c.m[s]);
+        } else {                                                              // plasma.cpp:420-424
+            ux = dv.xdiv(mx, rl);
+            uy = dv.xdiv(my, rl);
+        }
+        gt.note_velocity(ux);
+        gt.note_velocity(uy);
+    }
+}
+__device__ __forceinline__ void pair_velocity(GatedDiv& dv, CellGate& gt, D rla, D rlb, D uxa, D uya, D uxb, D uyb, D& upx, D& upy)
+{
+    if (rla < D(1e-10) && rlb < D(1e-10)) {                                   // plasma.cpp:426-449
+        upx = D(0.0); upy = D(0.0);
+    } else {
+        const D den = rla + rlb;
+        const D nx = rla * uxa + rlb * uxb, ny = rla * uya + rlb * uyb;
+        gt.note_den(den);
+        gt.note_num(nx);
+        gt.note_num(ny);
+        upx = dv.xdiv(nx, den);
+        upy = dv.xdiv(ny, den);
+        gt.note_pair_velocity(upx);
+        gt.note_pair_velocity(upy);
+    }
+}
+__device__ __forceinline__ void cell_update_macro(GatedDiv& dv, CellGate& gt, const D (&rl)[3], const D (&mx)[3], const D (&my)[3],
+                                                  const D (&tl)[3], D Ex, D Ey, const LbmConsts& c, CellMacro& m)
+{
+    gt.note_field(Ex);
+    gt.note_field(Ey);
+    static_for<3>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        species_velocity<s>(dv, gt, rl[s], mx[s], my[s], Ex, Ey, c, m.rho[s], m.ux[s], m.uy[s]);
+        m.T[s] = (rl[s] < D(1e-10)) ? D(0.0) : tl[s];
+        gt.note_temperature(m.T[s]);
+    });
+    static_for<3>([&](auto P) {
+        constexpr int p = decltype(P)::value;
+        constexpr int a = (p == 2) ? 1 : 0, b = (p == 0) ? 1 : 2;
+        pair_velocity(dv, gt, rl[a], rl[b], m.ux[a], m.uy[a], m.ux[b], m.uy[b], m.upx[p], m.upy[p]);
+    });
+    m.rho_q = charge_density(dv, m.rho[0], m.rho[1], c);
+}
+
 // Direction-independent pieces of the equilibrium bracket for one velocity (plasma.cpp:169-174,
 // 196-200):  K = u2*0.5*invcs2.
 struct VelSet {

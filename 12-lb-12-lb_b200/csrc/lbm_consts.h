@@ -54,6 +54,7 @@ struct LbmGeom {
     int pitch;            // doubles between consecutive rows of a population plane
     long long plane;      // doubles between consecutive planes = pitch * (NYl + 2)
     int wrap_y;           // 1: single slab, pull wraps y periodically; 0: halo rows are valid
+    int prefetch_rows;    // K1: distance in rows of the L2 prefetch (about one wave of CTAs ahead); 0 = none
 };
 
 } // namespace plbm

@@ -113,6 +113,8 @@ struct plbm_ctx {
     LbmGeom geom;
     cudaStream_t stream = nullptr;
     double* pop[2] = { nullptr, nullptr };   // ping-pong population planes
+    alignas(64) CUtensorMap pop_map[2];      // the same planes as TMA tensors (periodic lattices: the pull of K1 is done by the TMA engine)
+    bool tma = false;
     int cur = 0;                             // pop[cur] holds the current post-collision state
     double* Ex = nullptr; double* Ey = nullptr; double* rho_q = nullptr; double* phi = nullptr;
     double* macro[12] = {};                  // ux,uy (e,i,n), T (e,i,n), rho (e,i,n) in plbm.h field order (the set last written)
@@ -384,6 +386,11 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
                                        c->consts, c->geom, wa, c->stream));
         c->rim_cur ^= 1;
         c->identity_pull = false;
+    } else if (c->tma) {
+        const bool slabs = c->cfg.nranks > 1;
+        CUDA_TRY(launch_k1_tma(c->pop_map[c->cur], c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->e_stale ? c->phi : nullptr,
+                               slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr, c->rho_q, want_fields ? &mo : nullptr,
+                               c->consts, c->geom, c->stream));
     } else if (c->e_stale) {
         const bool slabs = c->cfg.nranks > 1;
         CUDA_TRY(launch_k1_fused_phi(c->pop[c->cur], c->pop[c->cur ^ 1], c->phi, slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr,
@@ -464,6 +471,7 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     c->geom.pitch = ((cfg->NX + 15) / 16) * 16;
     c->geom.plane = (long long)c->geom.pitch * (c->geom.NYl + 2);
     c->geom.wrap_y = (c->cfg.nranks == 1) ? 1 : 0;
+    c->geom.prefetch_rows = (cfg->bc_type == PLBM_BC_PERIODIC && !cfg->fields_only) ? k1_prefetch_rows(cfg->NX, c->geom.NYl) : 0;
     if (c->geom.plane >= (1LL << 31)) { delete c; return fail("plbm_create: slab too large for 32-bit plane offsets"); }
 
 #define TRY_OR_DESTROY(expr) do { if ((expr) != 0) { std::string keep = g_err; plbm_destroy(c); g_err = keep; return 1; } } while (0)
@@ -481,6 +489,12 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     for (int b = 0; b < 2 && !cfg->fields_only && !c->unfused; ++b) {
         TRY_OR_DESTROY(dev_alloc(c, &c->pop[b], pop_count));
         CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
+    }
+    if (c->pop[0] && !c->walls) {
+        // periodic lattices: K1 can pull through the TMA engine (PLBM_TMA=1; default: per-thread loads)
+        const char* e = std::getenv("PLBM_TMA");
+        c->tma = (e && e[0] && e[0] != '0');
+        for (int b = 0; b < 2 && c->tma; ++b) CUDA_OR_DESTROY(make_k1_tensor_map(&c->pop_map[b], c->pop[b], c->geom));
     }
     TRY_OR_DESTROY(dev_alloc(c, &c->Ex, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->Ey, n));

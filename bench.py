@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (tuning sweeps only)")
+    ap.add_argument("--parity-steps", type=int, default=8, help="time steps of the parity gate")
     return ap.parse_args()
 
 
@@ -159,6 +161,51 @@ def run_cpu_reference(nx: int, steps: int, poisson: str, threads: int):
     return nx * nx * steps / dt / 1e6, "port", {"loop_s": dt}
 
 
+def cpu_fields(nx: int, steps: int, poisson: str, threads: int):
+    """The 15 visualised fields + phi after `steps` time steps from the reference's initial condition, computed on the host:
+    by the UNMODIFIED reference (parity build: reference sources, -ffp-contract=off) where oracle/_ref holds it, else by
+    the C restatement.  Checker only -- nothing here is timed as, or shipped in, the product."""
+    from oracle import oracle as O
+    if O.have_reference("parity"):
+        _, dumps, _ = O.run_reference(nx, nx, steps, poisson=poisson, threads=threads, kind="parity", dump_steps=[steps - 1])
+        return dumps[steps - 1], "unmodified reference, parity build (oracle/_ref/ref_plasma_parity)"
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    o = O.PortOracle(nx, nx, poisson=poisson)
+    o.step(steps)
+    want = o.fields()
+    o.close()
+    return want, "C restatement (oracle/plasma_oracle.c)"
+
+
+def compare_fields(got: dict, want: dict):
+    """Number of fields that are not bit-identical (up to the sign of zero; NaN matches NaN), and the worst field-normalised error."""
+    import numpy as np
+    from oracle import oracle as O
+    bad, worst = [], 0.0
+    for n, w in want.items():
+        if n not in got:
+            continue
+        if not O.same_bits(got[n], w):
+            bad.append(n)
+            with np.errstate(all="ignore"):
+                den = float(np.nanmax(np.abs(w))) or 1.0
+                worst = max(worst, float(np.nanmax(np.abs(got[n] - w))) / den)
+    return bad, worst
+
+
+def parity_single(sim, nx: int, poisson: str, steps: int):
+    """N=1 gate: the benchmark's own workload, `steps` steps from the initial condition, GPU against the host checker."""
+    threads = os.cpu_count() or 1
+    want, checker = cpu_fields(nx, steps, poisson, threads)
+    sim.initialize()
+    sim.step(steps, want_fields=True)
+    got = sim.fields()
+    bad, worst = compare_fields(got, want)
+    return {"config": f"{nx}x{nx}, {poisson.upper()} Poisson, periodic (the timed workload)", "steps": steps, "fields": len(want),
+            "cells_compared": nx * nx * len(want), "mismatches": len(bad), "mismatched_fields": bad, "worst_normalised_error": worst,
+            "bar": "bit-identical (sign of zero aside)", "checker": checker}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -253,6 +300,10 @@ def main():
     line["clocks"] = clocks.summary()
     line["gpu_launches"] = t["launches"]
 
+    # ---- parity gate: the timed workload against the host checker ---------------------------
+    if not args.no_parity:
+        line["parity"] = parity_single(sim, nx, args.poisson, args.parity_steps)
+
     # ---- e2e: public API with host buffers -------------------------------------------------
     if not args.no_e2e:
         Ke = max(1, min(args.e2e_steps, K))
@@ -333,6 +384,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": threads, "kind": "unavailable", "sample": str(e)[:200]}
     sim.close()
     print(json.dumps(line), flush=True)
+    if line.get("parity", {}).get("mismatches"):
+        raise SystemExit("bench.py: the timed path is NOT bit-identical to the host checker (see the line's parity object)")
 
 
 SEGMENT = 48
@@ -389,10 +442,47 @@ def roofline(nx, cells, achieved, peak, peak_src, k1_ms, share):
             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": share}
 
 
+def parity_multi(args, P, torch, dist, world, rank, local_rank):
+    """N>1 gate, run BEFORE the timed region on the same ranks: slab-decomposed runs through BOTH exchange paths (peer memory over
+    NVLink, and NCCL messages) against the single-domain host checker, all 15 fields + phi bit for bit.  Cases: a lattice the
+    host checker finishes in seconds at the benchmark's slab height class (2048^2), and one whose rows do not divide evenly."""
+    cases = [(2048, args.parity_steps // 2 or 1), (200, 6)]
+    report, total_bad = [], 0
+    for nx, steps in cases:
+        want = checker = None
+        if rank == 0:
+            want, checker = cpu_fields(nx, steps, args.poisson, os.cpu_count() or 1)
+        for path in ("peer", "nccl"):
+            b = P.CudaSlabBackend(nx, nx, rank, world, poisson=args.poisson, device=local_rank)
+            try:
+                drv = P.SlabDriver(b, peer_memory=(path == "peer"))
+            except P.PlbmError as e:
+                b.close()
+                report.append({"lattice": f"{nx}x{nx}", "steps": steps, "path": path, "skipped": str(e)[:120]})
+                continue
+            drv.step(steps, want_fields=True)
+            b.sync()
+            full = drv.gather_fields(P.FIELD_NAMES)
+            rows = [b.slab_y0[r + 1] - b.slab_y0[r] for r in range(world)]
+            bad, worst = ([], 0.0)
+            if rank == 0:
+                bad, worst = compare_fields(full, want)
+            report.append({"lattice": f"{nx}x{nx}", "steps": steps, "path": path, "slab_rows": rows, "mismatches": len(bad),
+                           "mismatched_fields": bad, "worst_normalised_error": worst})
+            total_bad += len(bad)
+            drv.close()
+            b.close()
+    flag = torch.tensor([total_bad], device=f"cuda:{local_rank}")
+    dist.broadcast(flag, 0)
+    return {"config": f"{world} y-slabs, {args.poisson.upper()} Poisson, periodic; single-domain host checker", "fields": len(P.FIELD_NAMES),
+            "mismatches": int(flag.item()), "cases": report, "bar": "bit-identical (sign of zero aside)", "checker": checker}
+
+
 def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
     """Slab decomposition over `world` GPUs: halo send/recv + two all-to-alls per step (NCCL)."""
     import torch.distributed as dist
     nx = args.nx or WEAK_SIDES.get(world) or (int(2048 * world ** 0.5) // 64 * 64)
+    parity = None if args.no_parity else parity_multi(args, P, torch, dist, world, rank, local_rank)
     sampler = ClockSampler(local_rank).start()
     b = P.CudaSlabBackend(nx, nx, rank, world, poisson=args.poisson, device=local_rank)
     drv = P.SlabDriver(b)
@@ -427,6 +517,8 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
     line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + {transposes} + 1 phi row per side"
     line["clocks"] = clocks.summary()
     line["gpu_launches"] = K * (9 if drv.peer else 6)      # K1, halo pack/push, P1, P2, P3, unpack (+ 3 barrier kernels with peer memory)
+    if parity is not None:
+        line["parity"] = parity
     if not args.no_e2e:
         import ctypes as C
         Ke = max(1, min(args.e2e_steps, K))
@@ -457,6 +549,8 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
+    if parity is not None and parity["mismatches"]:
+        raise SystemExit("bench.py: the slab-decomposed path is NOT bit-identical to the host checker (see the line's parity object)")
 
 
 if __name__ == "__main__":

@@ -47,6 +47,24 @@ def test_reference_default_case_200x200(oracle, plbm):
     run_both(oracle, plbm, 200, 200, "fft", 200, {0, 1, 10, 50, 100, 150, 199})
 
 
+def test_benchmark_workload_2048x2048_whole_step(oracle, plbm):
+    """configs[2] of BASELINE.json, the lattice bench.py times: 8 whole time steps (K1 + spectral Poisson + field) at 2048x2048
+    against the UNMODIFIED reference compiled in place (parity build) where oracle/_ref holds it, else the C restatement:
+    all 15 visualised fields and the potential, bit for bit."""
+    NX, steps = 2048, 8
+    if oracle.have_reference("parity"):
+        _, dumps, _ = oracle.run_reference(NX, NX, steps, poisson="fft", kind="parity", dump_steps=[steps - 1])
+        want = dumps[steps - 1]
+    else:
+        o = oracle.PortOracle(NX, NX, poisson="fft")
+        o.step(steps)
+        want = o.fields()
+        o.close()
+    with plbm.PlasmaLBM(NX, NX, poisson="fft") as sim:
+        sim.step(steps, want_fields=True)
+        assert_fields_same(sim.fields(), want, f"{NX}x{NX}/fft/t={steps - 1}")
+
+
 def test_other_physical_parameters(oracle, plbm):
     run_both(oracle, plbm, 40, 40, "fft", 12, {0, 11}, Z_ion=2, A_ion=4, Ex_SI=3e-2, Ey_SI=-1e-2, T_i_SI=500.0)
 
