@@ -81,6 +81,8 @@ def load_library() -> C.CDLL:
     lib.plbm_pin_host.argtypes = [C.c_void_p, C.c_size_t]
     lib.plbm_unpin_host.argtypes = [C.c_void_p]
     lib.plbm_host_solve_poisson.argtypes = [C.c_void_p, dp, dp, dp]
+    lib.plbm_host_poisson_config.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+    lib.plbm_host_poisson_solver.argtypes = [C.c_void_p, C.c_int, dp]
     lib.plbm_step_timed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
     lib.plbm_local_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -213,6 +215,18 @@ class PlasmaLBM:
         Ey = np.zeros_like(rho_q) if Ey is None else np.ascontiguousarray(Ey, dtype=np.float64).copy()
         _check(self.lib, self.lib.plbm_host_solve_poisson(self._h, _dptr(rho_q), _dptr(Ex), _dptr(Ey)), "plbm_host_solve_poisson")
         return Ex, Ey
+
+    # poisson::SolvePoisson_{GS,SOR,FFT,9point} and their *_Periodic variants on host arrays (plbm_host_poisson_solver)
+    SOLVER_CODES = {"gs": 1, "sor": 2, "fft": 3, "nps": 4, "gs_periodic": 5, "sor_periodic": 6, "nps_periodic": 7}
+
+    def poisson_solver(self, solver: str, rho_q, omega: float = 1.8, bc: str = "periodic"):
+        """One call of the named solver on a fields-only context (rho_q -> phi, warm-started; the potential stays in the
+        context: fields(["phi"])).  Type, boundary and omega are per call, as in the reference."""
+        code = self.SOLVER_CODES[solver]
+        rho_q = np.ascontiguousarray(rho_q, dtype=np.float64)
+        base = {5: 1, 6: 2, 7: 4}.get(code, code)          # the PoissonType the reference's caller would pass
+        _check(self.lib, self.lib.plbm_host_poisson_config(self._h, base, BC[bc], omega), "plbm_host_poisson_config")
+        _check(self.lib, self.lib.plbm_host_poisson_solver(self._h, code, _dptr(rho_q)), "plbm_host_poisson_solver")
 
     def fetch_begin(self, out: np.ndarray, nfields: int = len(FIELD_NAMES)):
         """Start copying the last step's first `nfields` fields into out[nfields, NY_local, NX] (ideally pinned memory)

@@ -1,4 +1,4 @@
-// k1_kernel.cuh -- K1: one pass per time step over all three species, f and g (kernel template; instantiated by
+// k1_kernel.cuh -- K1: one pass per time step over all three species, f and g (kernel templates; instantiated by
 // k1_fused.cu for periodic lattices and k1_walls.cu for bounce-back walls).
 //
 // Replaces five full-grid sweeps of the reference with one kernel:
@@ -12,17 +12,23 @@
 // step at their own cell, so streaming is the shifted read f_i(x) <- src_i(x - c_i).  The kernel
 // writes post-collision values of this step to `dst` at its own cell (aligned, coalesced), plus
 // rho_q for the Poisson solve and, on request, the 12 moment fields the visualiser consumes.
-// Algorithmic traffic: 54*8 read + 54*8 written + Ex,Ey 16 + rho_q 8 = 888 B per cell and step.
+// Algorithmic traffic: 54*8 read + 54*8 written + phi 8 (or Ex,Ey 16) + rho_q 8 = 880 (888) B per cell and step.
 //
-// One thread owns one cell.  The 54 pulled populations are parked in shared memory (one column per
-// thread, conflict-free).  The cell is then processed by k1_cell<FastDiv>: moments, then a ROLLED
-// loop over the five direction axes (two opposite directions each) so that the ~2.7 k FP64
-// instructions per cell come from a loop body that fits the instruction cache.  FastDiv records
-// whether every division stayed inside the domain where its 2/3/9-instruction sequence is exact;
-// if not (never on physical data), the cell is recomputed out of line with the reference's literal
-// arithmetic (literal_cell.cuh).
+// One thread owns one cell.  The 54 pulled populations are parked in shared memory (the "stash", one column per thread,
+// conflict-free) while the moments are formed, then read again species by species for the collisions: a ROLLED loop over the
+// four axes that carry two opposite directions (its body, ~4.5 KB of code, stays in the instruction cache) and the rest
+// direction with everything resolved at compile time.  Divisions use the 2/3/8-instruction sequences of exact_math.cuh; a
+// per-cell gate (CellGate) proves them exact from ~90 noted values per cell ("K1 gate"), and a cell outside
+// the gate (never on physical data) is recomputed out of line with the reference's literal arithmetic (literal_cell.cuh).
+//
+// Three kernels share the cell code:
+//   k1_fused_kernel   periodic lattices, every thread pulls its own 54 values (LDG -> STS); one CTA per 64-cell tile
+//   k1_walls_kernel   bounce-back walls (walls.cuh), same structure
+//   k1_pool_kernel    periodic lattices, PERSISTENT warps: the pull is done by the TMA engine into a pool of stash buffers,
+//                     and a warp asks for its next tile while it still computes the current one (no load phase)
 #pragma once
 #include <cuda.h>
+#include <cstdint>
 #include "k1_fused.h"
 #include "lbm_cell.cuh"
 #include "literal_cell.cuh"
@@ -33,12 +39,6 @@ namespace plbm {
 #ifndef PLBM_K1_THREADS
 #define PLBM_K1_THREADS 64
 #endif
-#ifndef PLBM_K1_PAIR
-#define PLBM_K1_PAIR 1              // 1: both directions of an axis in one straight-line block
-#endif
-#ifndef PLBM_K1_GATE
-#define PLBM_K1_GATE 1              // 1: per-cell gate (CellGate); 0: a validity record per division (FastDiv)
-#endif
 #ifndef PLBM_K1_MIN_BLOCKS
 #define PLBM_K1_MIN_BLOCKS 6
 #endif
@@ -46,27 +46,30 @@ namespace plbm {
 #define PLBM_K1_CARVEOUT (-1)       // preferred shared-memory carve-out in percent; -1: leave the choice to the driver
 #endif
 #ifndef PLBM_K1_PREFETCH
-#define PLBM_K1_PREFETCH 1          // 1: every CTA asks L2 for the row segments a CTA one wave later will pull
+#define PLBM_K1_PREFETCH 1          // 1: every CTA asks L2 for the row segments a later CTA will pull (k1_fused_kernel)
 #endif
-#ifndef PLBM_K1_LDG
-#define PLBM_K1_LDG 0               // how the populations are read: 0 ld.global.nc, 1 ld.global.cg (L2 only), 2 ld.global.cs (streaming)
+#ifndef PLBM_K1_UNROLL
+#define PLBM_K1_UNROLL 0            // 1: all five axes unrolled (20 % fewer instructions, ~60 KB of code per cell: measured slower)
 #endif
 constexpr int K1_THREADS = PLBM_K1_THREADS;
 
-// Parked populations: slot of (species*2 + kind, direction) in the CTA's stash, one column per thread.  Direction-major, so that
-// the six distributions that share a pull offset are one contiguous TMA box (k1_tma_kernel below).
-__host__ __device__ constexpr int stash_slot(int sk, int dir) { return (dir * (2 * NSPEC) + sk) * K1_THREADS; }
-
-__device__ __forceinline__ double k1_load(const double* p)
-{
-#if PLBM_K1_LDG == 1
-    return __ldcg(p);
-#elif PLBM_K1_LDG == 2
-    return __ldcs(p);
-#else
-    return __ldg(p);
-#endif
-}
+// Where a parked population lives in the stash, relative to the thread's own pointer.
+//   ColumnLayout  [direction][species*2+kind][thread of the CTA]
+//   PoolLayout    k1_pool_kernel: nine TMA boxes (one per direction) of six rows of POOL_BOX_W doubles; a thread reads column
+//                 lane + 1 of a box whose direction has c_x != 0 (the box starts two cells early / at the tile, see there)
+struct ColumnLayout {
+    __host__ __device__ static constexpr int slot(int sk, int dir) { return (dir * (2 * NSPEC) + sk) * K1_THREADS; }
+};
+constexpr int POOL_TILE = 32;                                   // cells per tile = one warp
+constexpr int POOL_BOX_W = POOL_TILE + 2;                       // box width: tile + the two cells the +-1 pull offsets need
+constexpr int POOL_DIR_STRIDE = 208;                            // doubles between the boxes of two directions (6 * 34 = 204, padded to 128 B)
+constexpr int POOL_BUF_DOUBLES = NQ * POOL_DIR_STRIDE;          // 1872 doubles = 14 976 B per stash buffer
+struct PoolLayout {
+    __host__ __device__ static constexpr int slot(int sk, int dir)
+    {
+        return dir * POOL_DIR_STRIDE + sk * POOL_BOX_W + ((dir == 0 || dir == 2 || dir == 4) ? 0 : 1);
+    }
+};
 
 struct K1Out {
     double* __restrict__ dst;     // population planes, already offset to this cell
@@ -76,141 +79,8 @@ struct K1Out {
     long long cidx;
 };
 
-template <class DV, bool WRITE_MACRO>
-__device__ __forceinline__ void k1_cell(DV& dv, const double* __restrict__ stash, D Ex, D Ey, const K1Out& o, const LbmConsts& c)
-{
-    // ---- UpdateMacro ------------------------------------------------------------------------
-    CellMacro m;
-    {
-        D rl[3], mx[3], my[3], tl[3];
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            D f[NQ], g[NQ];
-            #pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                f[i] = D(stash[stash_slot(s * 2 + 0, i)]);
-                g[i] = D(stash[stash_slot(s * 2 + 1, i)]);
-            }
-            rl[s] = sum9(f); mx[s] = moment_x(f); my[s] = moment_y(f); tl[s] = sum9(g);
-        });
-        cell_update_macro(dv, rl, mx, my, tl, Ex, Ey, c, m);
-    }
-    *o.rho_q = m.rho_q.v;
-    if constexpr (WRITE_MACRO) {
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            o.mo.ux[s][o.cidx] = m.ux[s].v; o.mo.uy[s][o.cidx] = m.uy[s].v;
-            o.mo.T[s][o.cidx] = m.T[s].v;   o.mo.rho[s][o.cidx] = m.rho[s].v;
-        });
-    }
-
-    // ---- collisions, species by species (small live state per species) -----------------------
-    // Every species needs three equilibrium velocities: its own and those of its two pairs
-    // (plasma.cpp:195-304).  Directions: axis 0..3 carry two opposite directions, axis 4 is rest.
-    static_for<3>([&](auto S) {
-        constexpr int s = decltype(S)::value;
-        constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
-        const D vx[3] = { m.ux[s], m.upx[p0], m.upx[p1] };
-        const D vy[3] = { m.uy[s], m.upy[p0], m.upy[p1] };
-        const D u2 = vx[0] * vx[0] + vy[0] * vy[0];                           // collisions.cpp:98-100
-        D K[3];                                                               // u2*0.5*invcs2, plasma.cpp:199   (E3)
-        K[0] = u2 * D(c.hinvcs2);
-        K[1] = (vx[1] * vx[1] + vy[1] * vy[1]) * D(c.hinvcs2);
-        K[2] = (vx[2] * vx[2] + vy[2] * vy[2]) * D(c.hinvcs2);
-        D AB2[3];
-        thermal_cell_terms<s>(m.rho[s], c, AB2);
-        const D rhoh = D(0.5) * m.rho[s];
-        D uE = D(0.0);
-        if constexpr (s < 2) uE = vx[0] * Ex + vy[0] * Ey;                    // collisions.cpp:157,162
-
-        // Guo prefactor per weight class (4/9, 1/9, 1/36), collisions.cpp:154,159 -- three independent chains
-        D pref3[3] = { D(0.0), D(0.0), D(0.0) };
-        if constexpr (s < 2) {
-            #pragma unroll
-            for (int wc = 0; wc < 3; ++wc) pref3[wc] = guo_prefactor<s>(dv, wc, m.rho[s], c);
-        }
-
-        #pragma unroll 1
-        for (int axis = 0; axis < 5; ++axis) {
-            const int wclass = (axis < 2) ? 1 : (axis < 4 ? 2 : 0);
-            const AxisSel sel = axis_select(axis);
-            const D wr = D(c.w[wclass]) * m.rho[s];
-            const D wT = D(c.w[wclass]) * m.T[s];
-            BracketParts bp[3];
-            #pragma unroll
-            for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot(sel, vx[j], vy[j]), c);
-            D pref = D(0.0), X = D(0.0), cE = D(0.0);
-            if constexpr (s < 2) {
-                cE = axis_dot(sel, Ex, Ey);
-                pref = (wclass == 1) ? pref3[1] : (wclass == 2 ? pref3[2] : pref3[0]);
-                X = dv.cdiv(bp[0].cu * cE, c.cs2);                             // (c.u)(c.E)/cs2
-            }
-            // one direction of this axis: NEG = false is the axis' first direction, true its opposite
-            auto direction = [&](auto NEG, const int dir, const D fv, const D gv) {
-                constexpr bool neg = decltype(NEG)::value;
-                D b[3];
-                #pragma unroll
-                for (int j = 0; j < 3; ++j) b[j] = bracket_value<neg>(bp[j], K[j]);
-                D force = D(0.0);
-                if constexpr (s < 2) force = pref * guo_bracket<neg>(X, cE, uE);   // collisions.cpp:154-163
-                D fnew, gnew;
-                collide_species_dir<s>(dv, fv, gv, b, wr, wT, AB2, rhoh, u2, force, c, fnew, gnew);
-                dv.note_output(fnew);
-                dv.note_output(gnew);
-                o.dst[((s * 2 + 0) * NQ + dir) * o.plane] = fnew.v;
-                o.dst[((s * 2 + 1) * NQ + dir) * o.plane] = gnew.v;
-            };
-            const int d0 = (axis == 4) ? 0 : (axis < 2 ? axis + 1 : axis + 3);   // first direction of the axis; the opposite is d0 + 2
-#if PLBM_K1_PAIR
-            // both directions of the axis in one straight-line block: six independent division chains
-            const D f0 = D(stash[stash_slot(s * 2 + 0, d0)]), g0 = D(stash[stash_slot(s * 2 + 1, d0)]);
-            if (axis != 4) {
-                const D f1 = D(stash[stash_slot(s * 2 + 0, d0 + 2)]), g1 = D(stash[stash_slot(s * 2 + 1, d0 + 2)]);
-                direction(std::false_type{}, d0, f0, g0);
-                direction(std::true_type{}, d0 + 2, f1, g1);
-            } else {
-                direction(std::false_type{}, d0, f0, g0);
-            }
-#else
-            const int nsign = (axis == 4) ? 1 : 2;
-            #pragma unroll 1
-            for (int sg = 0; sg < nsign; ++sg) {
-                const int dir = d0 + 2 * sg;
-                const D fv = D(stash[stash_slot(s * 2 + 0, dir)]);
-                const D gv = D(stash[stash_slot(s * 2 + 1, dir)]);
-                if (sg) direction(std::true_type{}, dir, fv, gv);
-                else direction(std::false_type{}, dir, fv, gv);
-            }
-#endif
-        }
-    });
-}
-
-// ---- the same cell with the per-cell gate (exact_math.cuh: GatedDiv + CellGate) -------------------------------------------
-// No record per division: the gate notes the inputs (in the kernel's load loop), the macroscopic quantities and the
-// outputs, and DESIGN.md ("K1 gate") proves every fast division of the cell exact from those.  With PLBM_K1_UNROLL the five
-// direction axes are compile-time constants: c.v is a move, an addition or a subtraction, the weight class, the store offsets and
-// the rest direction's bracket 1 - K are resolved by the compiler, and nothing is selected or masked at run time.
-#ifndef PLBM_K1_UNROLL
-#define PLBM_K1_UNROLL 0
-#endif
-// With the axes unrolled the collision code of one cell is ~60 KB of straight-line instructions, twice the SM's instruction
-// cache: warps that drift apart fetch it from L2 again and again (measured: slower than the rolled loop although it issues
-// 20 % fewer instructions).  PLBM_K1_SYNC keeps the warps of a CTA together: 1 = a CTA barrier after every species, 2 = after
-// every direction axis, so that a line of code is fetched once per CTA, not once per warp.  TMA kernel only (all threads stay alive).
-#ifndef PLBM_K1_SYNC
-#define PLBM_K1_SYNC 0
-#endif
-template <int LEVEL>
-__device__ __forceinline__ void k1_sync_point()
-{
-#if PLBM_K1_SYNC
-    if constexpr (PLBM_K1_SYNC >= LEVEL) __syncthreads();
-#endif
-}
-
 // Second read of a parked population (the first was for the moments).  Volatile so that the compiler really reads shared
-// memory again instead of keeping all 54 values alive in registers and local memory across the moments (it spills otherwise).
+// memory again instead of keeping values alive in registers and local memory across the moments (it spills otherwise).
 __device__ __forceinline__ D stash_reload(const double* p)
 {
     double v;
@@ -228,7 +98,9 @@ __device__ __forceinline__ D axis_dot_ct(D vx, D vy)
     else { static_assert(AXIS == 3, "axis 4 is the rest direction"); return vy - vx; }
 }
 
-template <int S, int AXIS>
+// One axis with its direction(s) known at compile time: c.v is a move, an addition or a subtraction, the weight class and the
+// store offsets are constants, and the rest direction's bracket is 1 - K.
+template <int S, int AXIS, class L>
 __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const double* __restrict__ stash, const CellMacro& m,
                                            const D (&vx)[3], const D (&vy)[3], const D (&K)[3], const D (&AB2)[3], D rhoh, D u2,
                                            D uE, const D (&pref3)[3], D Ex, D Ey, const K1Out& o, const LbmConsts& c)
@@ -238,7 +110,7 @@ __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const dou
     const D wr = D(c.w[wclass]) * m.rho[S];
     const D wT = D(c.w[wclass]) * m.T[S];
     auto finish = [&](const int dir, const D (&b)[3], D force) {
-        const D fv = stash_reload(stash + stash_slot(S * 2 + 0, dir)), gv = stash_reload(stash + stash_slot(S * 2 + 1, dir));
+        const D fv = stash_reload(stash + L::slot(S * 2 + 0, dir)), gv = stash_reload(stash + L::slot(S * 2 + 1, dir));
         D fnew, gnew;
         collide_species_dir<S>(dv, fv, gv, b, wr, wT, AB2, rhoh, u2, force, c, fnew, gnew);
         gt.note_output(fnew);
@@ -276,9 +148,15 @@ __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const dou
     }
 }
 
-template <bool WRITE_MACRO>
+struct NoHook {
+    template <int S> __device__ __forceinline__ void at_axis(int) {}
+};
+
+// The whole cell.  L: stash layout.  `hook.at_axis<s>(axis)` runs at the top of every iteration of the axis loop of species s
+// (the pool kernel asks for its next tile at one of them).
+template <bool WRITE_MACRO, class L, class Hook>
 __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const double* __restrict__ stash, D Ex, D Ey, const K1Out& o,
-                                              const LbmConsts& c)
+                                              const LbmConsts& c, Hook& hook)
 {
     // ---- UpdateMacro ------------------------------------------------------------------------
     CellMacro m;
@@ -289,8 +167,8 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
             D f[NQ], g[NQ];
             #pragma unroll
             for (int i = 0; i < NQ; ++i) {
-                f[i] = D(stash[stash_slot(s * 2 + 0, i)]);
-                g[i] = D(stash[stash_slot(s * 2 + 1, i)]);
+                f[i] = D(stash[L::slot(s * 2 + 0, i)]);
+                g[i] = D(stash[L::slot(s * 2 + 1, i)]);
             }
             #pragma unroll
             for (int i = 0; i < NQ; ++i) { gt.note_input(f[i].v); gt.note_input(g[i].v); }
@@ -308,7 +186,8 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
         });
     }
 
-    // ---- collisions, species by species ---------------------------------------------------------
+    // ---- collisions, species by species (small live state per species) -----------------------
+    // Every species needs three equilibrium velocities: its own and those of its two pairs (plasma.cpp:195-304).
     static_for<3>([&](auto S) {
         constexpr int s = decltype(S)::value;
         constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
@@ -331,15 +210,14 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
         }
 #if PLBM_K1_UNROLL
         static_for<5>([&](auto AX) {
-            k1_axis_ct<s, decltype(AX)::value>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
-            k1_sync_point<2>();
+            k1_axis_ct<s, decltype(AX)::value, L>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
         });
-        k1_sync_point<1>();
 #else
         // four axes with two opposite directions each in a rolled loop (its body fits the instruction cache), then the rest
         // direction with everything resolved at compile time (c = 0: no dot products, bracket 1 - K)
         #pragma unroll 1
         for (int axis = 0; axis < 4; ++axis) {
+            hook.template at_axis<s>(axis);
             const AxisSel sel = axis_select(axis);
             const D w = (axis < 2) ? D(c.w[1]) : D(c.w[2]);
             const D wr = w * m.rho[s];
@@ -368,19 +246,20 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
                 o.dst[((s * 2 + 1) * NQ + dir) * o.plane] = gnew.v;
             };
             const int d0 = (axis < 2) ? axis + 1 : axis + 3;                  // first direction of the axis; the opposite is d0 + 2
-            const D f0 = D(stash[stash_slot(s * 2 + 0, d0)]), g0 = D(stash[stash_slot(s * 2 + 1, d0)]);
-            const D f1 = D(stash[stash_slot(s * 2 + 0, d0 + 2)]), g1 = D(stash[stash_slot(s * 2 + 1, d0 + 2)]);
+            // both directions of the axis in one straight-line block: six independent division chains
+            const D f0 = D(stash[L::slot(s * 2 + 0, d0)]), g0 = D(stash[L::slot(s * 2 + 1, d0)]);
+            const D f1 = D(stash[L::slot(s * 2 + 0, d0 + 2)]), g1 = D(stash[L::slot(s * 2 + 1, d0 + 2)]);
             direction(std::false_type{}, d0, f0, g0);
             direction(std::true_type{}, d0 + 2, f1, g1);
         }
-        k1_axis_ct<s, 4>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
+        k1_axis_ct<s, 4, L>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
 #endif
     });
 }
 
 // Out-of-line recomputation of one cell with the reference's literal arithmetic (literal_cell.cuh): taken when the
-// validity record of the fast path trips (operands outside FastDiv's domain, non-finite values).
-template <bool WRITE_MACRO>
+// gate trips (operands outside the fast divisions' domain, non-finite values).
+template <bool WRITE_MACRO, class L>
 static __device__ __noinline__ void k1_cell_literal(const double* stash, double Ex, double Ey, double* dst, long long plane, double* rho_q,
                                                     const MacroOut* mo, long long cidx, const LbmConsts* c)
 {
@@ -388,8 +267,8 @@ static __device__ __noinline__ void k1_cell_literal(const double* stash, double 
     D f[3][NQ], g[3][NQ];
     for (int s = 0; s < 3; ++s)
         for (int i = 0; i < NQ; ++i) {
-            f[s][i] = D(stash[stash_slot(s * 2 + 0, i)]);
-            g[s][i] = D(stash[stash_slot(s * 2 + 1, i)]);
+            f[s][i] = D(stash[L::slot(s * 2 + 0, i)]);
+            g[s][i] = D(stash[L::slot(s * 2 + 1, i)]);
         }
     LitMacro m;
     lit_update_macro(f, g, D(Ex), D(Ey), *c, m);
@@ -411,15 +290,41 @@ static __device__ __noinline__ void k1_cell_literal(const double* stash, double 
     }
 }
 
+// Gate, fast path and -- outside the gate -- the literal recomputation of one cell whose populations are parked at `stash`.
+// The fallback is skipped when every population input is zero or NaN and a raw density is NaN (CellGate::all_nan): then all 54
+// outputs are NaN on either path (each species is coupled to both others through the pair velocities) and the moments and
+// rho_q are NaN or the exact zeros of an empty species.  This keeps a lattice that the reference's own dynamics have driven to
+// NaN ("Divergence of the reference") at full speed.
+template <bool WRITE_MACRO, class L, class Hook>
+__device__ __forceinline__ void k1_cell_checked(const double* __restrict__ stash, double Ex, double Ey, const K1Out& o, const MacroOut* mo,
+                                                const LbmConsts& c, Hook& hook)
+{
+    CellGate gt;
+    GatedDiv dv;
+    k1_cell_gated<WRITE_MACRO, L>(dv, gt, stash, D(Ex), D(Ey), o, c, hook);
+    if (!gt.ok()) k1_cell_literal<WRITE_MACRO, L>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, mo, o.cidx, &c);
+}
+
 #ifdef PLBM_K1_MAXNREG
 #define PLBM_K1_BOUNDS __maxnreg__(PLBM_K1_MAXNREG)
 #else
 #define PLBM_K1_BOUNDS __launch_bounds__(K1_THREADS, PLBM_K1_MIN_BLOCKS)
 #endif
 
-// E_FROM_PHI: the field is not read from the Ex/Ey arrays but formed from the potential exactly as
-// poisson::ComputeElectricField_Periodic forms it (src/poisson.cpp:589-607) -- Exf is phi [NYl][NX], Eyf/Ezf the
-// neighbouring slabs' boundary rows (nullptr: wrap inside the array).  Saves the K3 sweep and 8 B per cell here.
+// E = -grad(phi) formed exactly as poisson::ComputeElectricField_Periodic forms it (src/poisson.cpp:589-607): phi is [NYl][NX],
+// below/above the neighbouring slabs' boundary rows (nullptr: wrap inside the array).  Saves the K3 sweep and 8 B per cell.
+__device__ __forceinline__ void field_from_phi(const double* __restrict__ phi, const double* __restrict__ below_row,
+                                               const double* __restrict__ above_row, int x, int y, int xm, int xp, const LbmGeom& g,
+                                               double& Ex, double& Ey)
+{
+    const double* row = phi + (long long)y * g.NX;
+    const double* below = (y > 0) ? row - g.NX : (below_row ? below_row : phi + (long long)(g.NYl - 1) * g.NX);
+    const double* above = (y < g.NYl - 1) ? row + g.NX : (above_row ? above_row : phi);
+    Ex = __dmul_rn(-0.5, __dsub_rn(__ldg(row + xp), __ldg(row + xm)));
+    Ey = __dmul_rn(-0.5, __dsub_rn(__ldg(above + x), __ldg(below + x)));
+}
+
+// E_FROM_PHI: Exf is phi, Eyf/Ezf the boundary rows below/above (field_from_phi); else Exf, Eyf are the field arrays.
 template <bool WRITE_MACRO, bool E_FROM_PHI>
 __global__ void PLBM_K1_BOUNDS
 k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
@@ -428,15 +333,8 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g)
 {
     extern __shared__ double stash_all[];
-#if PLBM_K1_SYNC
-    // every thread reaches every barrier: threads beyond the end of the row shadow its last cell (same loads into the same
-    // column of the stash, same results stored to the same addresses) instead of leaving
-    const int col = min((int)threadIdx.x, g.NX - 1 - (int)(blockIdx.x * K1_THREADS));
-#else
-    const int col = threadIdx.x;
-#endif
-    double* stash = stash_all + col;                  // column of this thread
-    const int x = blockIdx.x * K1_THREADS + col;
+    double* stash = stash_all + threadIdx.x;          // column of this thread
+    const int x = blockIdx.x * K1_THREADS + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= g.NX) return;
 
@@ -454,8 +352,8 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
 
 #if PLBM_K1_PREFETCH
     // The pull is one round trip to HBM that nothing in this CTA can hide.  Shorten it for a later CTA instead: thread p < 54 asks
-    // L2 for this tile's segment of plane p in the row `g.prefetch_rows` further on (about one wave of CTAs ahead in launch order),
-    // so that the CTA which pulls it finds it in L2.  Every segment of every row is requested exactly once per step.
+    // L2 for this tile's segment of plane p in the row `g.prefetch_rows` further on, so that the CTA which pulls it finds it
+    // in L2.  Every segment of every row is requested at most once per step.
     if (g.prefetch_rows > 0 && threadIdx.x < NPLANES) {
         int yp = y + g.prefetch_rows;
         if (yp >= g.NYl && g.wrap_y) yp -= g.NYl;
@@ -467,38 +365,20 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
         }
     }
 #endif
-#if PLBM_K1_GATE
-    CellGate gt;
-#else
-    unsigned nan_key = 0u;                             // max over the f inputs of 2*|high word|
-#endif
     // (ptxas hoists all 54 loads above the first store: one round trip to memory per cell)
     #pragma unroll
     for (int sk = 0; sk < 2 * NSPEC; ++sk) {
         const double* p = src + (long long)(sk * NQ) * g.plane;
         double v[NQ];
         #pragma unroll
-        for (int i = 0; i < NQ; ++i) v[i] = k1_load(p + i * g.plane + off[i]);
+        for (int i = 0; i < NQ; ++i) v[i] = __ldg(p + i * g.plane + off[i]);
         #pragma unroll
-        for (int i = 0; i < NQ; ++i) stash[stash_slot(sk, i)] = v[i];
-#if !PLBM_K1_GATE
-        if ((sk & 1) == 0) {                           // f populations: remember whether any of them is a NaN
-            #pragma unroll
-            for (int i = 0; i < NQ; ++i) { const unsigned hi = (unsigned)__double2hiint(v[i]); nan_key = max(nan_key, hi + hi); }
-        }
-#endif
+        for (int i = 0; i < NQ; ++i) stash[ColumnLayout::slot(sk, i)] = v[i];
     }
     const long long cidx = (long long)y * g.NX + x;    // scalar fields are flat x + NX*y
     double Ex, Ey;
-    if constexpr (E_FROM_PHI) {
-        const double* row = Exf + (long long)y * g.NX;
-        const double* below = (y > 0) ? row - g.NX : (Eyf ? Eyf : Exf + (long long)(g.NYl - 1) * g.NX);
-        const double* above = (y < g.NYl - 1) ? row + g.NX : (Ezf ? Ezf : Exf);
-        Ex = __dmul_rn(-0.5, __dsub_rn(__ldg(row + xp), __ldg(row + xm)));
-        Ey = __dmul_rn(-0.5, __dsub_rn(__ldg(above + x), __ldg(below + x)));
-    } else {
-        Ex = __ldg(Exf + cidx); Ey = __ldg(Eyf + cidx);
-    }
+    if constexpr (E_FROM_PHI) field_from_phi(Exf, Eyf, Ezf, x, y, xm, xp, g, Ex, Ey);
+    else { Ex = __ldg(Exf + cidx); Ey = __ldg(Eyf + cidx); }
 
     K1Out o;
     o.dst = dst + (long long)r0o + x;
@@ -506,33 +386,13 @@ k1_fused_kernel(const double* __restrict__ src, double* __restrict__ dst,
     o.rho_q = rho_q + cidx;
     o.mo = mo;
     o.cidx = cidx;
-
-#if PLBM_K1_GATE
-    // Outside the gate the cell is redone with the literal arithmetic -- unless every population input is zero or NaN and a
-    // raw density is NaN: then all 54 outputs are NaN on either path (each species is coupled to both others through the
-    // pair velocities) and the moments and rho_q are NaN or the exact zeros of an empty species.  This keeps a lattice that the
-    // reference's own dynamics have driven to NaN ("Divergence of the reference") at full speed.
-    GatedDiv dv;
-    k1_cell_gated<WRITE_MACRO>(dv, gt, stash, D(Ex), D(Ey), o, c);
-    if (!gt.ok()) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, &mo, o.cidx, &c);
-#else
-    FastDiv dv;
-    k1_cell<FastDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), o, c);
-    // Outside FastDiv's domain the cell is redone with the literal arithmetic -- unless an f input is a (quiet) NaN and no tiny
-    // numerator was seen: then every population output and rho_q is NaN on either path (each species is coupled to both
-    // others through the pair velocities), and the only finite outputs, the moments of the NaN-free species, come from
-    // divisions by a density >= 1e-10 whose numerators the record covers.  This keeps a lattice that the reference's own
-    // dynamics have driven to NaN ("Divergence of the reference") at full speed.
-    const bool nan_input = nan_key > 0xffe00000u;
-    if (!dv.ok() && !(nan_input && dv.numerators_ok())) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, &mo, o.cidx, &c);
-#endif
+    NoHook hook;
+    k1_cell_checked<WRITE_MACRO, ColumnLayout>(stash, Ex, Ey, o, &mo, c, hook);
 }
 
 
-// K1 with bounce-back walls: same cell work, the pull at the top follows walls.cuh.  A separate kernel so that the periodic
-// one above stays exactly as tuned (register allocation is sensitive to anything that moves in it).
-// bounce-back boundaries (streaming::StreamingBounceBack, src/streaming.cpp:66-112,150-196) as the pull at the top, see
-// walls.cuh; single slab only.
+// K1 with bounce-back walls: same cell work, the pull at the top follows walls.cuh (streaming::StreamingBounceBack,
+// src/streaming.cpp:66-112,150-196, restated as a pull); single slab only.
 template <bool WRITE_MACRO>
 __global__ void PLBM_K1_BOUNDS
 k1_walls_kernel(const double* __restrict__ src, double* __restrict__ dst,
@@ -541,17 +401,12 @@ k1_walls_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g, const WallArgs wa)
 {
     extern __shared__ double stash_all[];
-    double* stash = stash_all + threadIdx.x;          // column of this thread: stash[p * K1_THREADS]
+    double* stash = stash_all + threadIdx.x;          // column of this thread
     const int x = blockIdx.x * K1_THREADS + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= g.NX) return;
 
     const int r0o = (y + 1) * g.pitch;
-#if PLBM_K1_GATE
-    CellGate gt;
-#else
-    unsigned nan_key = 0u;                             // max over the f inputs of 2*|high word|
-#endif
     {
         // per destination slot: the cell and direction whose post-collision value lands here, or nothing (stale)
         const bool rim = (x == 0 || x == g.NX - 1 || y == 0 || y == g.NYl - 1);
@@ -586,16 +441,10 @@ k1_walls_kernel(const double* __restrict__ src, double* __restrict__ dst,
                 }
             }
             #pragma unroll
-            for (int i = 0; i < NQ; ++i) stash[stash_slot(sk, i)] = v[i];
-            if ((sk & 1) == 0) {
-#if !PLBM_K1_GATE
+            for (int i = 0; i < NQ; ++i) stash[ColumnLayout::slot(sk, i)] = v[i];
+            if ((sk & 1) == 0 && rim) {                // this step's pre-collision f: the stale values of the next pull
                 #pragma unroll
-                for (int i = 0; i < NQ; ++i) { const unsigned hi = (unsigned)__double2hiint(v[i]); nan_key = max(nan_key, hi + hi); }
-#endif
-                if (rim) {                             // this step's pre-collision f: the stale values of the next pull
-                    #pragma unroll
-                    for (int i = 0; i < NQ; ++i) wa.rim_next[((long long)((sk >> 1) * NQ + i)) * wa.nrim + ridx] = v[i];
-                }
+                for (int i = 0; i < NQ; ++i) wa.rim_next[((long long)((sk >> 1) * NQ + i)) * wa.nrim + ridx] = v[i];
             }
         }
     }
@@ -608,38 +457,61 @@ k1_walls_kernel(const double* __restrict__ src, double* __restrict__ dst,
     o.rho_q = rho_q + cidx;
     o.mo = mo;
     o.cidx = cidx;
-
-#if PLBM_K1_GATE
-    // Outside the gate the cell is redone with the literal arithmetic -- unless every population input is zero or NaN and a
-    // raw density is NaN: then all 54 outputs are NaN on either path (each species is coupled to both others through the
-    // pair velocities) and the moments and rho_q are NaN or the exact zeros of an empty species.  This keeps a lattice that the
-    // reference's own dynamics have driven to NaN ("Divergence of the reference") at full speed.
-    GatedDiv dv;
-    k1_cell_gated<WRITE_MACRO>(dv, gt, stash, D(Ex), D(Ey), o, c);
-    if (!gt.ok()) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, &mo, o.cidx, &c);
-#else
-    FastDiv dv;
-    k1_cell<FastDiv, WRITE_MACRO>(dv, stash, D(Ex), D(Ey), o, c);
-    // Outside FastDiv's domain the cell is redone with the literal arithmetic -- unless an f input is a (quiet) NaN and no tiny
-    // numerator was seen: then every population output and rho_q is NaN on either path (each species is coupled to both
-    // others through the pair velocities), and the only finite outputs, the moments of the NaN-free species, come from
-    // divisions by a density >= 1e-10 whose numerators the record covers.  This keeps a lattice that the reference's own
-    // dynamics have driven to NaN ("Divergence of the reference") at full speed.
-    const bool nan_input = nan_key > 0xffe00000u;
-    if (!dv.ok() && !(nan_input && dv.numerators_ok())) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, &mo, o.cidx, &c);
-#endif
+    NoHook hook;
+    k1_cell_checked<WRITE_MACRO, ColumnLayout>(stash, Ex, Ey, o, &mo, c, hook);
 }
 
 static __host__ __device__ constexpr size_t k1_smem_bytes() { return sizeof(double) * NPLANES * K1_THREADS; }
 
-// ---- K1 with the pull done by the TMA engine ----------------------------------------------------------------------------------
-// The population planes are described to the hardware as ONE 4-D tensor  [sk = species*2+kind][direction][storage row][x]
-// (strides 9*plane, plane, pitch, 1; x extent NX, so the padding of a row is out of bounds).  The pull of direction i is then
-// a box {K1_THREADS, 1, 1, 6} at (x0 - cx_i, row(y - cy_i), i, 0): six 8*K1_THREADS-byte row segments, one per distribution,
-// landing contiguously in the stash.  One elected thread issues the nine boxes of the CTA's tile and everybody waits on one
-// mbarrier: no LDG, no STS, no address arithmetic, no staging registers in the compute threads, and the loads do not pass
-// through L1.  The periodic wrap in x is not expressible as a box (out-of-bounds elements arrive as zeros): the two cells at
-// x = 0 and x = NX-1 fetch their three wrapped neighbours per distribution themselves after the wait.
+
+// ---- K1 with persistent warps and a TMA-filled pool of stash buffers -----------------------------------------------------------
+// What limits k1_fused_kernel once the instruction count is down: every CTA starts with one round trip to HBM that its two warps
+// can only wait for (long_scoreboard 0.68 per issue = 13 % of the warp time at 12 warps per SM, profiles/r2_k1_sweeps.md), and
+// a second stash per CTA to pull ahead does not fit in shared memory.  Here the warps are persistent and independent:
+//   * a tile is 32 consecutive cells of a row = one warp; warp gw of the grid runs tiles gw, gw + G, gw + 2G, ...
+//   * the SM's shared memory is a POOL of POOL_NBUF stash buffers for POOL_WARPS warps (15 for 12): a warp computes out of one
+//     buffer and, before its last species (72 % through the tile), takes a free buffer and has the TMA engine fill it with
+//     its NEXT tile; at the end of the tile it returns the old buffer.  With the three spare buffers held for the last quarter
+//     of a tile each, most warps never wait for memory; a warp that finds no free buffer reuses its own and waits as before.
+//   * the planes are ONE 4-D tensor [sk][direction][storage row][x] (strides 9*plane, plane, pitch, 1; x extent NX, so the
+//     padding of a row and the cells beyond the periodic edge are out of bounds = zero-filled).  The pull of direction i is a box
+//     {34, 1, 1, 6} at row(y - cy_i): FP64 boxes must start at an even x (16-byte alignment; an odd start raises an illegal
+//     instruction on B200, scratch/tma/tma_test2.cu), so the box starts at x0 - 2 for c_x = +1 and at x0 otherwise, and a
+//     thread reads column lane + 1 when c_x != 0 (PoolLayout).  One lane issues the nine boxes of a tile onto one mbarrier.
+//   * the periodic wrap in x is not expressible as a box: the cells x = 0 and x = NX-1 fetch their three wrapped neighbours per
+//     distribution themselves after the wait.
+// No LDG/STS, address arithmetic or staging registers for the pull, no CTA-wide barrier after start-up, nothing through L1.
+#ifndef PLBM_POOL_WARPS
+#define PLBM_POOL_WARPS 12
+#endif
+constexpr int POOL_WARPS = PLBM_POOL_WARPS;                     // 12 warps x 168 registers = the SM's register file
+constexpr int POOL_THREADS = POOL_WARPS * 32;
+constexpr int POOL_NBUF = 15;                                   // 15 x 14 976 B + barriers <= 227 KB
+constexpr unsigned POOL_TILE_BYTES = NQ * (2 * NSPEC) * POOL_BOX_W * sizeof(double);   // bytes the nine boxes deliver
+
+// Loop state of one warp.  It lives in shared memory, not in registers: the cell code needs all 168 registers a thread can have
+// at 12 warps per SM, and anything else kept live across it is paid for in recomputed FP64 products.
+struct PoolWarp {
+    int next_tile;                                              // the tile after the current one, -1: none
+    int next_buf;                                               // buffer that tile is being pulled into, -1: none yet
+    unsigned next_parity;                                       // parity of that buffer's barrier
+    int pad;
+    double Ex[POOL_TILE], Ey[POOL_TILE];                        // field at the cells of the next tile
+};
+struct PoolShared {
+    alignas(128) double buf[POOL_NBUF][POOL_BUF_DOUBLES];
+    alignas(8) unsigned long long full[POOL_NBUF];              // mbarrier per buffer: the tile has landed
+    PoolWarp warp[POOL_WARPS];
+    unsigned fills[POOL_NBUF];                                  // how often the buffer has been filled (parity of its barrier)
+    unsigned free_mask;                                         // bit b: buffer b is free
+    // kernel arguments the out-of-line helper needs
+    const CUtensorMap* tmap;
+    const LbmGeom* g;
+    const double *Exf, *Eyf, *Ezf;
+    int e_from_phi, tiles_per_row;
+};
+static __host__ __device__ constexpr size_t k1_pool_smem_bytes() { return sizeof(PoolShared) + 128; }
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void tma_load_box4(void* dst, const void* tmap, int c0, int c1, int c2, int c3, unsigned long long* bar)
@@ -650,7 +522,6 @@ __device__ __forceinline__ void tma_load_box4(void* dst, const void* tmap, int c
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
 {
@@ -665,97 +536,189 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     } while (!done);
 }
 
-static constexpr size_t k1_tma_smem_bytes() { return k1_smem_bytes() + 16; }     // + the mbarrier
-
-template <bool WRITE_MACRO, bool E_FROM_PHI>
-__global__ void PLBM_K1_BOUNDS
-k1_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ src, double* __restrict__ dst,
-              const double* __restrict__ Exf, const double* __restrict__ Eyf, const double* __restrict__ Ezf,
-              double* __restrict__ rho_q, const __grid_constant__ MacroOut mo,
-              const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g)
+__device__ __forceinline__ PoolShared& pool_shared()
 {
-    extern __shared__ __align__(128) double stash_all[];
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash_all + NPLANES * K1_THREADS);
-    const int x0 = blockIdx.x * K1_THREADS;
-#if PLBM_K1_SYNC
-    // every thread reaches every barrier: threads beyond the end of the row shadow its last cell (same column of the stash, same
-    // results stored to the same addresses) instead of leaving
-    const int col = min((int)threadIdx.x, g.NX - 1 - x0);
-#else
-    const int col = threadIdx.x;
-#endif
-    double* stash = stash_all + col;                  // column of this thread
-    const int x = x0 + col;
-    const int y = blockIdx.y;
-    int rm = y, rp = y + 2;                            // storage rows of y-1 and y+1 (halo rows: storage row = y + 1)
+    extern __shared__ unsigned char pool_raw[];
+    return *reinterpret_cast<PoolShared*>((reinterpret_cast<uintptr_t>(pool_raw) + 127) & ~(uintptr_t)127);
+}
+
+// One lane: arm buffer b's barrier and have the TMA engine pull tile `tile` into it.  Returns the parity to wait for.
+__device__ __forceinline__ unsigned pool_issue(PoolShared& sh, int b, int tile)
+{
+    const LbmGeom& g = *sh.g;
+    const int y = tile / sh.tiles_per_row, x0 = (tile - y * sh.tiles_per_row) * POOL_TILE;
+    int rm = y, rp = y + 2;                            // storage rows of y-1 and y+1 (storage row = y + 1)
     if (g.wrap_y) {
         if (y == 0) rm = g.NYl;
         if (y == g.NYl - 1) rp = 1;
     }
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (unsigned)k1_smem_bytes());
-        // direction i pulls from (x - cx_i, y - cy_i): cx = 0,1,0,-1,0,1,-1,-1,1   cy = 0,0,1,0,-1,1,1,-1,-1
-        const int bx[NQ] = { x0, x0 - 1, x0, x0 + 1, x0, x0 - 1, x0 + 1, x0 + 1, x0 - 1 };
-        const int br[NQ] = { y + 1, y + 1, rm, y + 1, rp, rm, rm, rp, rp };
-        #pragma unroll
-        for (int i = 0; i < NQ; ++i) tma_load_box4(stash_all + stash_slot(0, i), &tmap, bx[i], br[i], i, 0, bar);
-    }
-    __syncthreads();                                   // the barrier's initialisation is visible to the waiting threads
-#if !PLBM_K1_SYNC
-    if (x >= g.NX) return;
-#endif
-
-    const long long cidx = (long long)y * g.NX + x;    // scalar fields are flat x + NX*y
-    const int xm = (x == 0) ? g.NX - 1 : x - 1;
-    const int xp = (x == g.NX - 1) ? 0 : x + 1;
-    double Ex, Ey;
-    if constexpr (E_FROM_PHI) {
-        const double* row = Exf + (long long)y * g.NX;
-        const double* below = (y > 0) ? row - g.NX : (Eyf ? Eyf : Exf + (long long)(g.NYl - 1) * g.NX);
-        const double* above = (y < g.NYl - 1) ? row + g.NX : (Ezf ? Ezf : Exf);
-        Ex = __dmul_rn(-0.5, __dsub_rn(__ldg(row + xp), __ldg(row + xm)));
-        Ey = __dmul_rn(-0.5, __dsub_rn(__ldg(above + x), __ldg(below + x)));
-    } else {
-        Ex = __ldg(Exf + cidx); Ey = __ldg(Eyf + cidx);
-    }
-    const int r0o = (y + 1) * g.pitch;
-
-    mbar_wait(bar, 0);
-    if (x == 0 || x == g.NX - 1) {
-        // periodic wrap in x: the box delivered zeros for the neighbour outside [0, NX)
-        const int rmo = rm * g.pitch, rpo = rp * g.pitch;
-        #pragma unroll 1
-        for (int sk = 0; sk < 2 * NSPEC; ++sk) {
-            const double* p = src + (long long)(sk * NQ) * g.plane;
-            if (x == 0) {
-                stash[stash_slot(sk, 1)] = __ldg(p + 1 * g.plane + r0o + xm);
-                stash[stash_slot(sk, 5)] = __ldg(p + 5 * g.plane + rmo + xm);
-                stash[stash_slot(sk, 8)] = __ldg(p + 8 * g.plane + rpo + xm);
-            }
-            if (x == g.NX - 1) {
-                stash[stash_slot(sk, 3)] = __ldg(p + 3 * g.plane + r0o + xp);
-                stash[stash_slot(sk, 6)] = __ldg(p + 6 * g.plane + rmo + xp);
-                stash[stash_slot(sk, 7)] = __ldg(p + 7 * g.plane + rpo + xp);
-            }
-        }
-    }
-#if PLBM_K1_SYNC
-    __syncthreads();                                   // shadowing threads read the edge cell's column
-#endif
-
-    K1Out o;
-    o.dst = dst + (long long)r0o + x;
-    o.plane = g.plane;
-    o.rho_q = rho_q + cidx;
-    o.mo = mo;
-    o.cidx = cidx;
-
-    CellGate gt;
-    GatedDiv dv;
-    k1_cell_gated<WRITE_MACRO>(dv, gt, stash, D(Ex), D(Ey), o, c);
-    if (!gt.ok()) k1_cell_literal<WRITE_MACRO>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, &mo, o.cidx, &c);
+    const unsigned parity = sh.fills[b] & 1u;
+    sh.fills[b] += 1u;
+    // order this thread's earlier generic-proxy accesses of the buffer (the previous tile's fix-up stores) before the engine's writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&sh.full[b], POOL_TILE_BYTES);
+    // direction i pulls from (x - cx_i, y - cy_i): cx = 0,1,0,-1,0,1,-1,-1,1   cy = 0,0,1,0,-1,1,1,-1,-1; box start x0 - 2 where cx = +1
+    const int bx[NQ] = { x0, x0 - 2, x0, x0, x0, x0 - 2, x0, x0, x0 - 2 };
+    const int br[NQ] = { y + 1, y + 1, rm, y + 1, rp, rm, rm, rp, rp };
+    #pragma unroll
+    for (int i = 0; i < NQ; ++i) tma_load_box4(&sh.buf[b][i * POOL_DIR_STRIDE], sh.tmap, bx[i], br[i], i, 0, &sh.full[b]);
+    return parity;
 }
 
+// One lane: take a free buffer (-1: none).
+__device__ __forceinline__ int pool_try_acquire(PoolShared& sh)
+{
+    unsigned m = *(volatile unsigned*)&sh.free_mask;
+    while (m) {
+        const int b = __ffs(m) - 1;
+        const unsigned seen = atomicCAS(&sh.free_mask, m, m & ~(1u << b));
+        if (seen == m) { __threadfence_block(); return b; }
+        m = seen;
+    }
+    return -1;
+}
+
+// The field at this lane's cell of tile `tile`, parked for the tile's start.
+__device__ __forceinline__ void pool_load_field(PoolShared& sh, PoolWarp& w, int tile)
+{
+    const LbmGeom& g = *sh.g;
+    const int lane = threadIdx.x & 31;
+    const int y = tile / sh.tiles_per_row, x = (tile - y * sh.tiles_per_row) * POOL_TILE + lane;
+    if (x < g.NX) {
+        double Ex, Ey;
+        const int xm = (x == 0) ? g.NX - 1 : x - 1, xp = (x == g.NX - 1) ? 0 : x + 1;
+        if (sh.e_from_phi) field_from_phi(sh.Exf, sh.Eyf, sh.Ezf, x, y, xm, xp, g, Ex, Ey);
+        else { const long long cidx = (long long)y * g.NX + x; Ex = __ldg(sh.Exf + cidx); Ey = __ldg(sh.Eyf + cidx); }
+        w.Ex[lane] = Ex; w.Ey[lane] = Ey;
+    }
+}
+
+// Asks for the warp's next tile: a free buffer, the nine boxes, and the field around the next cells.  Out of line and without
+// arguments (everything comes from shared memory), so that the call site inside the collision loop costs no registers.
+#ifndef PLBM_POOL_ASK_AXIS
+#define PLBM_POOL_ASK_AXIS 2
+#endif
+static __device__ __noinline__ void pool_ask()
+{
+    PoolShared& sh = pool_shared();
+    PoolWarp& w = sh.warp[threadIdx.x >> 5];
+    const int tile = w.next_tile;
+    if (tile < 0) return;
+    if ((threadIdx.x & 31) == 0) {
+        const int b = pool_try_acquire(sh);
+        if (b >= 0) { w.next_parity = pool_issue(sh, b, tile); w.next_buf = b; }
+    }
+    pool_load_field(sh, w, tile);
+}
+
+// Called at the top of every axis iteration: late in the current tile (axis PLBM_POOL_ASK_AXIS of the last species, 80-90 %
+// through it) the warp asks for its next tile.  A spare buffer is then held for the last 10-20 % of a tile, so the three spares
+// serve the twelve warps (12 x 0.15 = 1.8 in use on average) and the ~2 us that remain cover the round trip to HBM.
+struct PoolHook {
+    template <int S> __device__ __forceinline__ void at_axis(int axis)
+    {
+        if constexpr (S == 2) {
+            if (axis == PLBM_POOL_ASK_AXIS) pool_ask();
+        }
+    }
+};
+
+template <bool WRITE_MACRO, bool E_FROM_PHI>
+__global__ void __launch_bounds__(POOL_THREADS, 1)
+k1_pool_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ src, double* __restrict__ dst,
+               const double* __restrict__ Exf, const double* __restrict__ Eyf, const double* __restrict__ Ezf,
+               double* __restrict__ rho_q, const __grid_constant__ MacroOut mo,
+               const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g)
+{
+    PoolShared& sh = pool_shared();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_row = (g.NX + POOL_TILE - 1) / POOL_TILE;
+    const int count = per_row * g.NYl;
+    const int G = gridDim.x * POOL_WARPS;
+
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < POOL_NBUF; ++b) { mbar_init(&sh.full[b], 1); sh.fills[b] = 0u; }
+        sh.free_mask = ((1u << POOL_NBUF) - 1u) & ~((1u << POOL_WARPS) - 1u);      // warp w starts with buffer w
+        sh.tmap = &tmap; sh.g = &g; sh.Exf = Exf; sh.Eyf = Eyf; sh.Ezf = Ezf;
+        sh.e_from_phi = E_FROM_PHI ? 1 : 0; sh.tiles_per_row = per_row;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int tile = blockIdx.x * POOL_WARPS + warp;         // consecutive tiles run on consecutive warps of consecutive SMs
+    if (tile >= count) return;
+    int buf = warp;
+    unsigned parity = 0u;
+    PoolWarp& ws = sh.warp[warp];
+    if (lane == 0) parity = pool_issue(sh, buf, tile);
+    pool_load_field(sh, ws, tile);
+
+    #pragma unroll 1
+    for (;;) {
+        const int y = tile / per_row, x0 = (tile - y * per_row) * POOL_TILE;
+        const int x = x0 + lane;
+        const bool live = x < g.NX;
+        const int xc = live ? x : g.NX - 1;            // lanes beyond the end of the row idle; keep their addresses valid
+        const long long cidx = (long long)y * g.NX + xc;
+        const int r0o = (y + 1) * g.pitch;
+        double* stash = &sh.buf[buf][0] + lane;
+        __syncwarp();
+        const double Ex = ws.Ex[lane], Ey = ws.Ey[lane];  // loaded while the previous tile was computed (or before the loop)
+        __syncwarp();
+        if (lane == 0) { ws.next_tile = (tile + G < count) ? tile + G : -1; ws.next_buf = -1; }
+
+        parity = __shfl_sync(0xffffffffu, parity, 0);
+        mbar_wait(&sh.full[buf], parity);
+        if (live && (x == 0 || x == g.NX - 1)) {
+            // periodic wrap in x: the box delivered zeros for the neighbour outside [0, NX)
+            const int xm = (x == 0) ? g.NX - 1 : x - 1, xp = (x == g.NX - 1) ? 0 : x + 1;
+            int rm = y, rp = y + 2;
+            if (g.wrap_y) {
+                if (y == 0) rm = g.NYl;
+                if (y == g.NYl - 1) rp = 1;
+            }
+            const int rmo = rm * g.pitch, rpo = rp * g.pitch;
+            #pragma unroll 1
+            for (int sk = 0; sk < 2 * NSPEC; ++sk) {
+                const double* p = src + (long long)(sk * NQ) * g.plane;
+                if (x == 0) {
+                    stash[PoolLayout::slot(sk, 1)] = __ldg(p + 1 * g.plane + r0o + xm);
+                    stash[PoolLayout::slot(sk, 5)] = __ldg(p + 5 * g.plane + rmo + xm);
+                    stash[PoolLayout::slot(sk, 8)] = __ldg(p + 8 * g.plane + rpo + xm);
+                }
+                if (x == g.NX - 1) {
+                    stash[PoolLayout::slot(sk, 3)] = __ldg(p + 3 * g.plane + r0o + xp);
+                    stash[PoolLayout::slot(sk, 6)] = __ldg(p + 6 * g.plane + rmo + xp);
+                    stash[PoolLayout::slot(sk, 7)] = __ldg(p + 7 * g.plane + rpo + xp);
+                }
+            }
+        }
+        __syncwarp();                                  // next_tile is set before any lane can reach pool_ask
+
+        if (live) {
+            K1Out o;
+            o.dst = dst + (long long)r0o + x;
+            o.plane = g.plane;
+            o.rho_q = rho_q + cidx;
+            o.mo = mo;
+            o.cidx = cidx;
+            PoolHook hook;
+            k1_cell_checked<WRITE_MACRO, PoolLayout>(stash, Ex, Ey, o, &mo, c, hook);
+        }
+        __syncwarp();
+        // lane 0 (always live: x0 < NX) has been through pool_ask
+        const int next = ws.next_tile;
+        if (next < 0) break;
+        const int nb = ws.next_buf;
+        if (nb >= 0) {
+            if (lane == 0) { __threadfence_block(); atomicOr(&sh.free_mask, 1u << buf); }    // every lane has finished reading `buf`
+            buf = nb;
+            parity = ws.next_parity;
+        } else {
+            if (lane == 0) parity = pool_issue(sh, buf, next);                              // no spare buffer was free: pull into my own
+        }
+        tile = next;
+    }
+}
 
 } // namespace plbm

@@ -109,6 +109,7 @@ int plbm_set_error(const char* msg) { return fail("%s", msg); }
 
 struct plbm_ctx {
     plbm_config cfg;
+    int device = -1;                         // ordinal every launch of this context targets (entry points switch to it and back)
     LbmConsts consts;
     LbmGeom geom;
     cudaStream_t stream = nullptr;
@@ -128,6 +129,8 @@ struct plbm_ctx {
     double* series = nullptr;                // [NUM_SERIES][NUM_POINTS]
     double* staging = nullptr;               // 9*NX*NYl doubles for AoS transfers
     bool macro_valid = false;
+    bool halo_fresh = false;                 // slabs: the halo rows were filled by plbm_initialize / plbm_upload_state themselves (each rank
+                                             // writes every row its own cells pull from), so there is nothing to exchange until a step has run
     bool e_stale = false;                    // Ex/Ey arrays not materialised: K1 takes E = -grad(phi) from phi itself (fused periodic FFT path)
     bool poisson_called = false;             // call_once of reference src/poisson.cpp:34-41
     // spectral Poisson
@@ -167,6 +170,21 @@ struct plbm_ctx {
 };
 
 namespace {
+
+// Every extern "C" entry makes the context's device current for its own duration and restores the caller's: two contexts on
+// different GPUs can live in one process (plbm_group), and a caller that never selected the device still launches correctly.
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(const plbm_ctx* c)
+    {
+        if (c && c->device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != c->device)
+            switched = (cudaSetDevice(c->device) == cudaSuccess);
+    }
+    ~DevGuard() { if (switched) cudaSetDevice(prev); }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
 
 template <class T>
 int dev_alloc(plbm_ctx* c, T** p, size_t count)
@@ -281,11 +299,11 @@ int poisson_first_call(plbm_ctx* c)
     return 0;
 }
 
-// one of poisson::SolvePoisson_{GS,SOR,FFT,9point}: rho_q -> phi
+// one of poisson::SolvePoisson_{GS,SOR,FFT,9point}[_Periodic]: rho_q -> phi
 int poisson_solver(plbm_ctx* c, int type, long long* launches)
 {
     if (type == PLBM_POISSON_FFT) {
-        if (!c->fft.T1) return fail("spectral Poisson was not set up for this context (poisson_type must be FFT at creation)");
+        if (!c->fft.T1 && build_fft(c)) return 1;            // plan and tables on the first spectral request (host API: the type is per call)
         if (c->cfg.nranks != 1) return fail("several slabs: drive the Poisson stages with plbm_poisson_stage() around the all-to-all exchanges");
         CUDA_TRY(launch_poisson_rows_fwd(c->fft, c->rho_q, c->stream));
         CUDA_TRY(launch_poisson_cols(c->fft, c->stream));
@@ -293,10 +311,12 @@ int poisson_solver(plbm_ctx* c, int type, long long* launches)
         if (launches) *launches += 3;
         return 0;
     }
-    if (type == PLBM_POISSON_GS || type == PLBM_POISSON_SOR || type == PLBM_POISSON_NPS) {
+    const bool wrapped = (type == PLBM_POISSON_GS_PERIODIC || type == PLBM_POISSON_SOR_PERIODIC || type == PLBM_POISSON_NPS_PERIODIC);
+    if (type == PLBM_POISSON_GS || type == PLBM_POISSON_SOR || type == PLBM_POISSON_NPS || wrapped) {
         if (c->cfg.nranks != 1) return fail("the iterative Poisson solvers run on a single slab");
-        const int kind = (type == PLBM_POISSON_GS) ? 0 : (type == PLBM_POISSON_SOR ? 1 : 2);
-        CUDA_TRY(launch_poisson_iterative(kind, c->phi, c->rho_q, c->cfg.NX, c->cfg.NY, c->cfg.omega_sor, c->err_bits, c->iters_dev, c->stream));
+        const int kind = (type == PLBM_POISSON_GS || type == PLBM_POISSON_GS_PERIODIC) ? 0
+                       : (type == PLBM_POISSON_SOR || type == PLBM_POISSON_SOR_PERIODIC) ? 1 : 2;
+        CUDA_TRY(launch_poisson_iterative(kind, wrapped, c->phi, c->rho_q, c->cfg.NX, c->cfg.NY, c->cfg.omega_sor, c->err_bits, c->iters_dev, c->stream));
         if (launches) *launches += 1;
         return 0;
     }
@@ -388,7 +408,7 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
         c->identity_pull = false;
     } else if (c->tma) {
         const bool slabs = c->cfg.nranks > 1;
-        CUDA_TRY(launch_k1_tma(c->pop_map[c->cur], c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->e_stale ? c->phi : nullptr,
+        CUDA_TRY(launch_k1_pool(c->pop_map[c->cur], c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->e_stale ? c->phi : nullptr,
                                slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr, c->rho_q, want_fields ? &mo : nullptr,
                                c->consts, c->geom, c->stream));
     } else if (c->e_stale) {
@@ -402,6 +422,7 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
     if (launches) *launches += 1;
     c->cur ^= 1;
     c->macro_valid = want_fields;
+    c->halo_fresh = false;
     return 0;
 }
 
@@ -450,10 +471,14 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("plbm_create: no CUDA device (this library has no CPU path)");
+    int caller_device = 0;
+    CUDA_TRY(cudaGetDevice(&caller_device));
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{ caller_device };     // the caller's device is current again on return
     if (cfg->device >= 0) CUDA_TRY(cudaSetDevice(cfg->device));
 
     plbm_ctx* c = new plbm_ctx();
     c->cfg = *cfg;
+    c->device = cfg->device >= 0 ? cfg->device : caller_device;
     if (c->cfg.nranks <= 1) { c->cfg.nranks = 1; c->cfg.rank = 0; c->cfg.y0 = 0; c->cfg.NY_local = cfg->NY; }
     else {
         // the library owns the decomposition rule (plbm_slab_of); y0 / NY_local of the caller are ignored
@@ -491,9 +516,11 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
         CUDA_OR_DESTROY(cudaMemsetAsync(c->pop[b], 0, sizeof(double) * pop_count, c->stream));
     }
     if (c->pop[0] && !c->walls) {
-        // periodic lattices: K1 can pull through the TMA engine (PLBM_TMA=1; default: per-thread loads)
-        const char* e = std::getenv("PLBM_TMA");
-        c->tma = (e && e[0] && e[0] != '0');
+        // periodic lattices: PLBM_K1_POOL=1 runs K1 as persistent warps fed by the TMA engine (k1_pool_kernel) instead of the kernel
+        // in which every thread pulls its own populations (k1_fused_kernel).  Bit-identical, measured 20 % slower on B200
+        // (profiles/r2_k1_sweeps.md), so it is not the default.
+        const char* e = std::getenv("PLBM_K1_POOL");
+        c->tma = (e && e[0] == '1');
         for (int b = 0; b < 2 && c->tma; ++b) CUDA_OR_DESTROY(make_k1_tensor_map(&c->pop_map[b], c->pop[b], c->geom));
     }
     TRY_OR_DESTROY(dev_alloc(c, &c->Ex, n));
@@ -553,6 +580,7 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
 
 void plbm_destroy(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto e : c->events) cudaEventDestroy(e);
@@ -581,6 +609,7 @@ void plbm_destroy(plbm_ctx* c)
 
 int plbm_initialize(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_initialize: null context");
     if (c->unfused) {
         const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
@@ -612,11 +641,13 @@ int plbm_initialize(plbm_ctx* c)
     CUDA_TRY(cudaMemsetAsync(c->rho_q, 0, sizeof(double) * n, c->stream));
     c->poisson_called = false;
     c->macro_valid = false;
+    c->halo_fresh = true;
     return 0;
 }
 
 int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const g[3])
 {
+    DevGuard guard__(c);
     if (!c || !f || !g) return fail("plbm_upload_state: null argument");
     if (c->unfused) {
         const size_t ub = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
@@ -642,12 +673,17 @@ int plbm_upload_state(plbm_ctx* c, const double* const f[3], const double* const
             }
         }
     if (c->walls) c->identity_pull = true;
+    // On a slab the upload has also written the two halo rows (the cells of rows 0 and NYl-1 pull from them), while the rows that
+    // LEAVE the slab (directions 2/5/6 of storage row NYl, 4/7/8 of row 1) hold nothing new: an exchange now would overwrite the
+    // neighbours' correct halo rows with stale data, so plbm_halo_pack/push/unpack are no-ops until a step has run.
+    c->halo_fresh = true;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
 {
+    DevGuard guard__(c);
     if (!c || !f || !g) return fail("plbm_download_state: null argument");
     if (c->unfused) {
         const size_t ub = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl * NQ;
@@ -678,6 +714,7 @@ int plbm_download_state(plbm_ctx* c, double* const f[3], double* const g[3])
 
 int plbm_set_efield(plbm_ctx* c, const double* Ex, const double* Ey)
 {
+    DevGuard guard__(c);
     if (!c || !Ex || !Ey) return fail("plbm_set_efield: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     c->e_stale = false;
@@ -696,6 +733,7 @@ constexpr int GRAPH_MIN_STEPS = 24;
 
 int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_step: null context");
     if (c->cfg.nranks > 1) return fail("plbm_step: this context is one slab of %d; drive it with plbm_step_local / plbm_halo_* / plbm_poisson_stage", c->cfg.nranks);
     auto eager = [&](int from, int to) -> int {
@@ -737,6 +775,7 @@ int plbm_step(plbm_ctx* c, int nsteps, int want_fields)
 
 int plbm_sync(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_sync: null context");
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
@@ -744,6 +783,7 @@ int plbm_sync(plbm_ctx* c)
 
 int plbm_download_fields(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 {
+    DevGuard guard__(c);
     if (!c || !out) return fail("plbm_download_fields: null argument");
     if ((out[PLBM_F_EX] || out[PLBM_F_EY]) && materialise_efield(c)) return 1;
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
@@ -765,6 +805,7 @@ int plbm_download_fields(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 
 int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 {
+    DevGuard guard__(c);
     if (!c || !out) return fail("plbm_fetch_begin: null argument");
     if (c->fetch_pending) return fail("plbm_fetch_begin: the previous fetch was not completed with plbm_fetch_wait");
     if ((out[PLBM_F_EX] || out[PLBM_F_EY]) && materialise_efield(c)) return 1;
@@ -802,6 +843,7 @@ int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
 
 int plbm_frames_begin(plbm_ctx* c, float* const frames[PLBM_NUM_FRAMES], double* series)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_frames_begin: null context");
     if (c->fetch_pending) return fail("plbm_frames_begin: the previous fetch was not completed");
     if (!c->macro_valid) return fail("plbm_frames_begin: moment fields were not requested from the last plbm_step");
@@ -856,6 +898,7 @@ int plbm_unpin_host(void* p)
 
 int plbm_fetch_wait(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_fetch_wait: null context");
     if (!c->fetch_pending) return 0;
     CUDA_TRY(cudaEventSynchronize(c->ev_fetched));
@@ -865,6 +908,7 @@ int plbm_fetch_wait(plbm_ctx* c)
 
 int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, float* ms_k1, float* ms_poisson, long long* launches)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_step_timed: null context");
     if (nsteps < 1 || nsteps > 100000) return fail("plbm_step_timed: nsteps out of range");
     if (c->cfg.nranks > 1) return fail("plbm_step_timed: single-slab contexts only");
@@ -902,6 +946,7 @@ int plbm_step_timed(plbm_ctx* c, int nsteps, int want_fields, float* ms_total, f
 
 int plbm_host_solve_poisson(plbm_ctx* c, const double* rho_q, double* Ex, double* Ey)
 {
+    DevGuard guard__(c);
     if (!c || !rho_q || !Ex || !Ey) return fail("plbm_host_solve_poisson: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     CUDA_TRY(cudaMemcpyAsync(c->rho_q, rho_q, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -915,8 +960,22 @@ int plbm_host_solve_poisson(plbm_ctx* c, const double* rho_q, double* Ex, double
     return 0;
 }
 
+int plbm_host_poisson_config(plbm_ctx* c, int poisson_type, int bc_type, double omega_sor)
+{
+    DevGuard guard__(c);
+    if (!c) return fail("plbm_host_poisson_config: null context");
+    if (c->pop[0] || c->unfused) return fail("plbm_host_poisson_config: only for fields-only contexts (the time loop keeps the type it was created with)");
+    if (poisson_type < PLBM_POISSON_NONE || poisson_type > PLBM_POISSON_NPS) return fail("plbm_host_poisson_config: Poisson type %d", poisson_type);
+    if (bc_type != PLBM_BC_PERIODIC && bc_type != PLBM_BC_BOUNCEBACK) return fail("plbm_host_poisson_config: boundary type %d", bc_type);
+    c->cfg.poisson_type = poisson_type;
+    c->cfg.bc_type = bc_type;
+    c->cfg.omega_sor = omega_sor;
+    return 0;
+}
+
 int plbm_host_poisson_solver(plbm_ctx* c, int poisson_type, const double* rho_q)
 {
+    DevGuard guard__(c);
     if (!c || !rho_q) return fail("plbm_host_poisson_solver: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     if (poisson_first_call(c)) return 1;
@@ -928,6 +987,7 @@ int plbm_host_poisson_solver(plbm_ctx* c, int poisson_type, const double* rho_q)
 
 int plbm_host_efield(plbm_ctx* c, int bc_type, double* Ex, double* Ey)
 {
+    DevGuard guard__(c);
     if (!c || !Ex || !Ey) return fail("plbm_host_efield: null argument");
     const size_t bytes = sizeof(double) * (size_t)c->geom.NX * c->geom.NYl;
     if (poisson_first_call(c)) return 1;
@@ -956,26 +1016,32 @@ int plbm_slab_of(int NY, int rank, int nranks, int* y0, int* ny_local)
 
 int plbm_step_local(plbm_ctx* c, int want_fields)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_step_local: null context");
     return one_step(c, want_fields != 0, nullptr);
 }
 
 int plbm_halo_pack(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || c->cfg.nranks < 2) return fail("plbm_halo_pack: needs a multi-slab context");
+    if (c->halo_fresh) return 0;            // initialise / upload filled the halo rows: nothing to exchange (see plbm_upload_state)
     CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->halo_send_lo, c->halo_send_hi, c->geom, c->stream));
     return 0;
 }
 
 int plbm_halo_unpack(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || c->cfg.nranks < 2) return fail("plbm_halo_unpack: needs a multi-slab context");
+    if (c->halo_fresh) return 0;            // initialise / upload filled the halo rows: nothing to exchange (see plbm_upload_state)
     CUDA_TRY(launch_halo_unpack(c->pop[c->cur], c->halo_recv_lo, c->halo_recv_hi, c->geom, c->stream));
     return 0;
 }
 
 int plbm_poisson_stage(plbm_ctx* c, int stage)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_poisson_stage: null context");
     if (poisson_first_call(c)) return 1;
     const int type = c->cfg.poisson_type;
@@ -1001,16 +1067,24 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
     }
 }
 
+namespace {
+int ensure_peer_flags(plbm_ctx* c)
+{
+    if (c->flags) return 0;
+    if (dev_alloc(c, &c->flags, PLBM_MAX_RANKS)) return 1;
+    if (dev_alloc(c, &c->peer_timeout, 1)) return 1;
+    CUDA_TRY(cudaMemset(c->flags, 0, sizeof(unsigned long long) * PLBM_MAX_RANKS));
+    CUDA_TRY(cudaMemset(c->peer_timeout, 0, sizeof(int)));
+    return 0;
+}
+} // namespace
+
 int plbm_peer_export(plbm_ctx* c, void* blob)
 {
+    DevGuard guard__(c);
     if (!c || !blob) return fail("plbm_peer_export: null argument");
     if (c->cfg.nranks < 2 || !c->fft.T1) return fail("plbm_peer_export: needs a multi-slab context with the spectral Poisson solve");
-    if (!c->flags) {
-        if (dev_alloc(c, &c->flags, PLBM_MAX_RANKS)) return 1;
-        if (dev_alloc(c, &c->peer_timeout, 1)) return 1;
-        CUDA_TRY(cudaMemset(c->flags, 0, sizeof(unsigned long long) * PLBM_MAX_RANKS));
-        CUDA_TRY(cudaMemset(c->peer_timeout, 0, sizeof(int)));
-    }
+    if (ensure_peer_flags(c)) return 1;
     PeerBlob b;
     std::memset(&b, 0, sizeof(b));
     const void* bufs[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below, c->phi_above };
@@ -1026,6 +1100,7 @@ int plbm_peer_export(plbm_ctx* c, void* blob)
 
 int plbm_peer_attach(plbm_ctx* c, const void* blobs)
 {
+    DevGuard guard__(c);
     if (!c || !blobs) return fail("plbm_peer_attach: null argument");
     if (!c->flags) return fail("plbm_peer_attach: call plbm_peer_export first");
     if (c->peers) return 0;
@@ -1060,15 +1135,101 @@ int plbm_peer_attach(plbm_ctx* c, const void* blobs)
     return 0;
 }
 
+// Same wiring for slabs that live in ONE process (plbm_group): no IPC, the sibling contexts' pointers are used directly after
+// peer access between the devices has been enabled.  all[s] is the context of slab s (all[rank] == c).
+int plbm_peer_attach_local(plbm_ctx* c, plbm_ctx* const* all)
+{
+    DevGuard guard__(c);
+    if (!c || !all) return fail("plbm_peer_attach_local: null argument");
+    if (c->cfg.nranks < 2 || !c->fft.T1) return fail("plbm_peer_attach_local: needs a multi-slab context with the spectral Poisson solve");
+    if (c->peers) return 0;
+    const int R = c->cfg.nranks, me = c->cfg.rank, up = (me + 1) % R, down = (me + R - 1) % R;
+    for (int s = 0; s < R; ++s) {
+        plbm_ctx* o = all[s];
+        if (!o || o->cfg.rank != s || o->cfg.nranks != R || !o->fft.T1) return fail("plbm_peer_attach_local: context %d is not slab %d of %d", s, s, R);
+        if (!o->flags) return fail("plbm_peer_attach_local: slab %d has no flag buffer yet (plbm_peer_prepare_local on every slab first)", s);
+        if (s != me && o->device != c->device) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->device, o->device));
+            if (!can) return fail("plbm_peer_attach_local: device %d cannot access device %d", c->device, o->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return fail("cudaDeviceEnablePeerAccess(%d) failed: %s", o->device, cudaGetErrorString(e));
+        }
+        c->peer_t1.t1[s] = o->fft.T1;
+        c->peer_flags[s] = o->flags;
+        if (s == up) { c->up_halo_recv_lo = o->halo_recv_lo; c->up_phi_below = o->phi_below; }
+        if (s == down) { c->down_halo_recv_hi = o->halo_recv_hi; c->down_phi_above = o->phi_above; }
+    }
+    c->peers = true;
+    return 0;
+}
+int plbm_peer_prepare_local(plbm_ctx* c)
+{
+    DevGuard guard__(c);
+    if (!c) return fail("plbm_peer_prepare_local: null context");
+    return ensure_peer_flags(c);
+}
+
+// One whole time step of a slab with peers attached, `nsteps` times, in one call:
+//   K1, halo push, P1, BARRIER, halo unpack, P2 over peer memory, BARRIER, P3 + phi rows into the neighbours, BARRIER
+// (the sequence documented in plbm.h).  stage_ms, if given, receives the accumulated device time of the nine stages in that
+// order (CUDA events on the library's stream; at most the last 32 steps are timed).
+int plbm_step_peer(plbm_ctx* c, int nsteps, int want_fields, float* stage_ms)
+{
+    DevGuard guard__(c);
+    if (!c || !c->peers) return fail("plbm_step_peer: peer memory is not attached");
+    if (nsteps < 0) return fail("plbm_step_peer: nsteps = %d", nsteps);
+    constexpr int NS = 9, TIMED = 32;
+    std::vector<cudaEvent_t> ev;
+    const int first_timed = nsteps > TIMED ? nsteps - TIMED : 0;
+    if (stage_ms) {
+        ev.resize((size_t)(NS + 1) * (nsteps - first_timed));
+        for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    }
+    auto mark = [&](int t, int k) -> int {
+        if (!stage_ms || t < first_timed) return 0;
+        CUDA_TRY(cudaEventRecord(ev[(size_t)(t - first_timed) * (NS + 1) + k], c->stream));
+        return 0;
+    };
+    int rc = 0;
+    for (int t = 0; t < nsteps && !rc; ++t) {
+        rc = mark(t, 0) || one_step(c, want_fields && t == nsteps - 1, nullptr) || mark(t, 1)
+          || plbm_halo_push(c) || mark(t, 2)
+          || plbm_poisson_stage(c, 0) || mark(t, 3)
+          || plbm_peer_barrier(c) || mark(t, 4)
+          || plbm_halo_unpack(c) || mark(t, 5)
+          || plbm_poisson_stage(c, 4) || mark(t, 6)
+          || plbm_peer_barrier(c) || mark(t, 7)
+          || plbm_poisson_stage(c, 5) || mark(t, 8)
+          || plbm_peer_barrier(c) || mark(t, 9)
+          || plbm_poisson_stage(c, 3);
+    }
+    if (stage_ms && !rc) {
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("plbm_step_peer: stream synchronisation failed");
+        for (int t = first_timed; t < nsteps && !rc; ++t)
+            for (int k = 0; k < NS; ++k) {
+                float ms = 0.f;
+                const size_t b = (size_t)(t - first_timed) * (NS + 1);
+                if (cudaEventElapsedTime(&ms, ev[b + k], ev[b + k + 1]) == cudaSuccess) stage_ms[k] += ms;
+            }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 // halo rows straight into the neighbours' receive buffers / boundary rows of phi into the neighbours' copies
 int plbm_halo_push(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_halo_push: peer memory is not attached");
+    if (c->halo_fresh) return 0;            // initialise / upload filled the halo rows: nothing to exchange (see plbm_upload_state)
     CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->down_halo_recv_hi, c->up_halo_recv_lo, c->geom, c->stream));
     return 0;
 }
 int plbm_phi_rows_push(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_phi_rows_push: peer memory is not attached");
     const size_t row = sizeof(double) * c->cfg.NX;
     CUDA_TRY(cudaMemcpyAsync(c->up_phi_below, c->phi + (size_t)(c->geom.NYl - 1) * c->cfg.NX, row, cudaMemcpyDeviceToDevice, c->stream));
@@ -1078,6 +1239,7 @@ int plbm_phi_rows_push(plbm_ctx* c)
 
 int plbm_peer_detach(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_peer_detach: null context");
     if (c->stream) CUDA_TRY(cudaStreamSynchronize(c->stream));
     for (void*& m : c->peer_mapped) {
@@ -1090,6 +1252,7 @@ int plbm_peer_detach(plbm_ctx* c)
 
 int plbm_peer_barrier(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_peer_barrier: peer memory is not attached");
     PeerFlags pf;
     for (int s = 0; s < PLBM_MAX_RANKS; ++s) pf.f[s] = c->peer_flags[s];
@@ -1101,6 +1264,7 @@ int plbm_peer_barrier(plbm_ctx* c)
 
 int plbm_peer_check(plbm_ctx* c)
 {
+    DevGuard guard__(c);
     if (!c || !c->peers) return 0;
     int t = 0;
     CUDA_TRY(cudaMemcpyAsync(&t, c->peer_timeout, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1111,6 +1275,7 @@ int plbm_peer_check(plbm_ctx* c)
 
 int plbm_exchange_info(plbm_ctx* c, plbm_exchange* o)
 {
+    DevGuard guard__(c);
     if (!c || !o) return fail("plbm_exchange_info: null argument");
     std::memset(o, 0, sizeof(*o));
     const int R = c->cfg.nranks, nh = c->cfg.NY / 2 + 1;
@@ -1129,6 +1294,7 @@ int plbm_exchange_info(plbm_ctx* c, plbm_exchange* o)
 
 int plbm_local_rows(const plbm_ctx* c, int* y0, int* ny_local)
 {
+    DevGuard guard__(c);
     if (!c) return fail("plbm_local_rows: null context");
     if (y0) *y0 = c->cfg.y0;
     if (ny_local) *ny_local = c->geom.NYl;

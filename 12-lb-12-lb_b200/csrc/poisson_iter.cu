@@ -3,6 +3,7 @@
 //   poisson::SolvePoisson_GS       /root/reference/src/poisson.cpp:90-142    red-black Gauss-Seidel
 //   poisson::SolvePoisson_SOR      /root/reference/src/poisson.cpp:216-279   red-black SOR
 //   poisson::SolvePoisson_9point   /root/reference/src/poisson.cpp:429-483   4-colour 9-point Gauss-Seidel
+//   poisson::SolvePoisson_{GS,SOR,9point}_Periodic  /root/reference/src/poisson.cpp:146-211, 283-354, 487-546   same sweeps, all cells, wrapped
 //   poisson::ComputeElectricField  /root/reference/src/poisson.cpp:551-585   central differences + Neumann rim
 //
 // All three solvers sweep the interior 1..N-2 in place with phi = 0 on the rim, warm-started from
@@ -30,41 +31,57 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// kind 0 = GS, 1 = SOR (5-point, 2 colours), 2 = 9-point (4 colours)
-template <int KIND>
-__global__ void __launch_bounds__(256)
+// KIND 0 = GS, 1 = SOR (5-point, 2 colours), 2 = 9-point (4 colours).  PERIODIC: the *_Periodic variants (all cells, wrapped
+// neighbours; poisson.cpp:146-211, 283-354, 487-546), else the Dirichlet ones (interior cells, phi = 0 on the rim).
+// Work mapping: rows over CTAs, the cells of the current colour in a row over the CTA's threads (every second cell from the first
+// one of that colour): no thread visits a cell of another colour, no division or modulo per cell.
+// With an odd periodic extent two cells of one colour are neighbours across the wrap and the sweep is order-dependent -- in the
+// reference's own OpenMP loop as well; even extents (the only ones the reference's default lattices have) are bit-reproducible.
+constexpr int ITER_THREADS = 128;
+
+template <int KIND, bool PERIODIC>
+__global__ void __launch_bounds__(ITER_THREADS)
 poisson_iter_kernel(double* phi, const double* __restrict__ rho_q, int NX, int NY, double omega,
                     unsigned long long* __restrict__ err_bits /* [2] ping-pong */, int* __restrict__ iters_out)
 {
     cg::grid_group grid = cg::this_grid();
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long nthreads = (long long)gridDim.x * blockDim.x;
-    const int ix = NX - 2, iy = NY - 2;                       // interior extent
-    const long long ncell = (long long)(ix > 0 ? ix : 0) * (iy > 0 ? iy : 0);
+    const bool first_thread = (blockIdx.x == 0 && threadIdx.x == 0);
+    constexpr int lo = PERIODIC ? 0 : 1;
+    const int hx = PERIODIC ? NX : NX - 1, hy = PERIODIC ? NY : NY - 1;      // exclusive upper bounds of the swept cells
     constexpr int NCOL = (KIND == 2) ? 4 : 2;
     int iter = 0;
     for (; iter < ITER_MAX; ++iter) {
         unsigned long long* slot = err_bits + (iter & 1);
         double local = 0.0;
         for (int colour = 0; colour < NCOL; ++colour) {
-            for (long long t = tid; t < ncell; t += nthreads) {
-                const int i = 1 + (int)(t % ix), j = 1 + (int)(t / ix);
-                const bool mine = (KIND == 2) ? ((2 * (i & 1) + (j & 1)) == colour) : (((i + j) & 1) == colour);
-                if (!mine) continue;
-                const size_t c = (size_t)i + (size_t)NX * j;
-                const double old = phi[c];
-                double nw;
-                if (KIND == 2) {                                                     // poisson.cpp:459-466
-                    const double so = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + 1], phi[c - 1]), phi[c + NX]), phi[c - NX]);
-                    const double sd = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + NX + 1], phi[c + NX - 1]), phi[c - NX + 1]), phi[c - NX - 1]);
-                    nw = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(4.0, so), sd), __dmul_rn(6.0, rho_q[c])), 20.0);
-                } else {                                                             // poisson.cpp:106-110, 231-241
-                    const double nb = __dadd_rn(__dadd_rn(__dadd_rn(phi[c + 1], phi[c - 1]), phi[c + NX]), phi[c - NX]);
-                    const double gs = __dmul_rn(0.25, __dadd_rn(nb, rho_q[c]));
-                    nw = (KIND == 1) ? __dadd_rn(__dmul_rn(__dsub_rn(1.0, omega), old), __dmul_rn(omega, gs)) : gs;
+            // 2 colours: (i + j) & 1 == colour, every row has cells.  4 colours: 2*(i & 1) + (j & 1) == colour, every second row.
+            const int jstep = (KIND == 2) ? 2 : 1;
+            const int j0 = (KIND == 2) ? lo + ((lo ^ colour) & 1) : lo;
+            for (int j = j0 + jstep * (int)blockIdx.x; j < hy; j += jstep * (int)gridDim.x) {
+                const int ipar = (KIND == 2) ? (colour >> 1) : ((colour ^ j) & 1);           // parity of i in this row
+                const int i0 = lo + ((lo ^ ipar) & 1);
+                const int jn = PERIODIC ? (j + 1 == NY ? 0 : j + 1) : j + 1, js = PERIODIC ? (j == 0 ? NY - 1 : j - 1) : j - 1;
+                const double* rown = phi + (size_t)NX * jn;
+                const double* rows = phi + (size_t)NX * js;
+                double* row = phi + (size_t)NX * j;
+                for (int i = i0 + 2 * (int)threadIdx.x; i < hx; i += 2 * ITER_THREADS) {
+                    const int ie = PERIODIC ? (i + 1 == NX ? 0 : i + 1) : i + 1, iw = PERIODIC ? (i == 0 ? NX - 1 : i - 1) : i - 1;
+                    const double old = row[i];
+                    const double rq = rho_q[(size_t)NX * j + i];
+                    double nw;
+                    if (KIND == 2) {                                                     // poisson.cpp:459-466, 520-531
+                        const double so = __dadd_rn(__dadd_rn(__dadd_rn(row[ie], row[iw]), rown[i]), rows[i]);
+                        const double sd = __dadd_rn(__dadd_rn(__dadd_rn(rown[ie], rown[iw]), rows[ie]), rows[iw]);
+                        const double num = __dadd_rn(__dadd_rn(__dmul_rn(4.0, so), sd), __dmul_rn(6.0, rq));
+                        nw = PERIODIC ? __dmul_rn(num, 0.05) : __ddiv_rn(num, 20.0);     // the periodic variant multiplies by 0.05
+                    } else {                                                             // poisson.cpp:106-110, 231-241, 163-171, 301-313
+                        const double nb = __dadd_rn(__dadd_rn(__dadd_rn(row[ie], row[iw]), rown[i]), rows[i]);
+                        const double gs = __dmul_rn(0.25, __dadd_rn(nb, rq));
+                        nw = (KIND == 1) ? __dadd_rn(__dmul_rn(__dsub_rn(1.0, omega), old), __dmul_rn(omega, gs)) : gs;
+                    }
+                    row[i] = nw;
+                    local = fmax(local, fabs(__dsub_rn(nw, old)));
                 }
-                phi[c] = nw;
-                local = fmax(local, fabs(__dsub_rn(nw, old)));
             }
             if (colour == NCOL - 1) {                          // the barrier that ends the last colour also completes the reduction
                 local = warp_max(local);
@@ -72,12 +89,12 @@ poisson_iter_kernel(double* phi, const double* __restrict__ rho_q, int NX, int N
             }
             grid.sync();                                       // the next colour (or iteration) reads this colour's updates
             // the other slot was last read after the previous iteration's final barrier: every thread is past that now
-            if (colour == 0 && tid == 0) err_bits[(iter + 1) & 1] = 0ull;
+            if (colour == 0 && first_thread) err_bits[(iter + 1) & 1] = 0ull;
         }
         const double maxErr = __longlong_as_double((long long)*(volatile unsigned long long*)slot);
         if (maxErr < ITER_TOL) { ++iter; break; }              // poisson.cpp:137-140, 275-277, 479-481
     }
-    if (tid == 0 && iters_out) *iters_out = iter;
+    if (first_thread && iters_out) *iters_out = iter;
 }
 
 // poisson.cpp:556-563: interior central differences
@@ -108,23 +125,26 @@ __global__ void efield_rim_cols_kernel(double* __restrict__ Ex, double* __restri
     Ex[r + NX - 1] = Ex[r + NX - 2];   Ey[r + NX - 1] = Ey[r + NX - 2];
 }
 
-cudaError_t launch_poisson_iterative(int kind, double* phi, const double* rho_q, int NX, int NY, double omega,
+cudaError_t launch_poisson_iterative(int kind, bool periodic, double* phi, const double* rho_q, int NX, int NY, double omega,
                                      unsigned long long* err_bits, int* iters_out, cudaStream_t stream)
 {
-    void* fn = (kind == 0) ? (void*)poisson_iter_kernel<0> : (kind == 1) ? (void*)poisson_iter_kernel<1> : (void*)poisson_iter_kernel<2>;
+    void* fns[2][3] = { { (void*)poisson_iter_kernel<0, false>, (void*)poisson_iter_kernel<1, false>, (void*)poisson_iter_kernel<2, false> },
+                        { (void*)poisson_iter_kernel<0, true>, (void*)poisson_iter_kernel<1, true>, (void*)poisson_iter_kernel<2, true> } };
+    void* fn = fns[periodic ? 1 : 0][kind];
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0)) != cudaSuccess) return e;
-    const long long cells = (long long)(NX > 2 ? NX - 2 : 0) * (NY > 2 ? NY - 2 : 0);
-    long long want = (cells + 255) / 256;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ITER_THREADS, 0)) != cudaSuccess) return e;
+    // one CTA per swept row (per second row for the 4-colour sweep), all resident by construction; few CTAs keep the grid barrier cheap
+    const int rows = periodic ? NY : (NY > 2 ? NY - 2 : 0);
+    long long want = (kind == 2) ? (rows + 1) / 2 : rows;
     if (want < 1) want = 1;
-    const long long cap = (long long)sms * (per_sm > 2 ? 2 : per_sm);    // resident by construction, few CTAs: cheap grid barriers
+    const long long cap = (long long)sms * (per_sm > 2 ? 2 : per_sm);
     const int blocks = (int)(want < cap ? want : cap);
     if ((e = cudaMemsetAsync(err_bits, 0, 2 * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
     void* args[] = { &phi, &rho_q, &NX, &NY, &omega, &err_bits, &iters_out };
-    return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, stream);
+    return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(ITER_THREADS), args, 0, stream);
 }
 
 cudaError_t launch_efield_walls(const double* phi, double* Ex, double* Ey, int NX, int NY, cudaStream_t stream)

@@ -66,6 +66,7 @@ class CudaSlabBackend:
         lib.plbm_peer_barrier.argtypes = [C.c_void_p]
         lib.plbm_peer_check.argtypes = [C.c_void_p]
         lib.plbm_peer_detach.argtypes = [C.c_void_p]
+        lib.plbm_step_peer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
         lib.plbm_halo_push.argtypes = [C.c_void_p]
         lib.plbm_phi_rows_push.argtypes = [C.c_void_p]
         self.lib = lib
@@ -119,6 +120,18 @@ class CudaSlabBackend:
 
     def halo_push(self):
         _check(self.lib, self.lib.plbm_halo_push(self.sim._h), "plbm_halo_push")
+
+    STAGES = ("k1", "halo_push", "p1_rows_fwd", "barrier1", "halo_unpack", "p2_cols_peer", "barrier2", "p3_rows_inv_phi_rows", "barrier3")
+
+    def step_peer(self, nsteps: int, want_fields: bool = False, stage_ms=None):
+        """The whole peer-memory step sequence nsteps times in one library call (plbm_step_peer).  stage_ms: a dict that
+        receives the accumulated device time [ms] of the nine stages (STAGES; at most the last 32 steps are timed)."""
+        buf = (C.c_float * 9)() if stage_ms is not None else None
+        _check(self.lib, self.lib.plbm_step_peer(self.sim._h, nsteps, int(want_fields), buf), "plbm_step_peer")
+        if stage_ms is not None:
+            for k, name in enumerate(self.STAGES):
+                stage_ms[name] = stage_ms.get(name, 0.0) + float(buf[k])
+            stage_ms["timed_steps"] = stage_ms.get("timed_steps", 0) + min(nsteps, 32)
 
     def phi_rows_push(self):
         _check(self.lib, self.lib.plbm_phi_rows_push(self.sim._h), "plbm_phi_rows_push")
@@ -226,13 +239,18 @@ class SlabDriver:
             return []
         return works
 
-    def step(self, nsteps: int = 1, want_fields: bool = False, timing=None):
+    def step(self, nsteps: int = 1, want_fields: bool = False, timing=None, stage_ms=None):
         """nsteps time steps.  timing: optional list that receives one (start, end) CUDA event pair
-        around every fused collide-stream launch (CUDA backend only).
+        around every fused collide-stream launch (CUDA backend only).  stage_ms: optional dict for the per-stage device
+        times of the peer-memory path (CudaSlabBackend.step_peer).
 
         Order inside a step: the population halo exchange only feeds the NEXT step's K1, so it is
         started right after K1 and completed after the Poisson stages, which it overlaps."""
         b, d = self.b, self.dist
+        if self.peer and timing is None and hasattr(b, "step_peer"):
+            # no messages and no host round trip per kernel: the library issues the whole sequence itself
+            b.step_peer(nsteps, want_fields, stage_ms)
+            return
         with b.stream_context():
             for t in range(nsteps):
                 if timing is not None:
@@ -273,8 +291,10 @@ class SlabDriver:
                 b.halo_unpack()
 
     def refresh_halos(self):
-        """Exchange the population halo rows of the current state (after an upload; plbm_initialize fills
-        them itself from the global initial condition, for which this is a no-op in effect)."""
+        """Exchange the population halo rows of the current state.  Only a state that a time step produced has anything to
+        exchange: plbm_initialize and plbm_upload_state fill a slab's halo rows themselves (every rank writes each row its own
+        cells pull from), and the library turns the pack / push / unpack calls into no-ops until the next step -- an exchange
+        right after an upload would overwrite the neighbours' correct halo rows with rows the upload never wrote."""
         b = self.b
         with b.stream_context():
             if self.peer:

@@ -5,6 +5,7 @@
 #include "plbm.h"
 #include "visualize_frames.hpp"
 
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -36,8 +37,18 @@ LBmethod::LBmethod(const int _NSTEPS, const int _NX, const int _NY, const size_t
     cfg.rank = 0; cfg.nranks = 1; cfg.y0 = 0; cfg.NY_local = NY; cfg.device = -1;
     if (plbm_units_from_si(Z_ion, A_ion, Ex_SI, Ey_SI, T_e_SI_init, T_i_SI_init, T_n_SI_init, n_e_SI_init, n_n_SI_init, &cfg))
         raise("LBmethod: unit conversion");
-    if (plbm_create(&cfg, &ctx_)) raise("LBmethod: device state");
-    if (plbm_initialize(ctx_)) { plbm_destroy(ctx_); ctx_ = nullptr; raise("LBmethod: Initialize"); }
+    // PLBM_DEVICES=N: the same object on N GPUs (one context per device, slabs wired through peer memory, one host thread per device)
+    int ndev = 1;
+    if (const char* e = std::getenv("PLBM_DEVICES")) ndev = std::atoi(e);
+    const bool sliceable = poisson_type == poisson::PoissonType::FFT && bc_type == streaming::BCType::Periodic;
+    if (ndev > 1 && sliceable) {
+        if (plbm_group_create(&cfg, ndev, &group_)) raise("LBmethod: device state (PLBM_DEVICES)");
+        if (plbm_group_initialize(group_)) { plbm_group_destroy(group_); group_ = nullptr; raise("LBmethod: Initialize"); }
+    } else {
+        if (ndev > 1) std::cerr << "LBmethod: PLBM_DEVICES=" << ndev << " ignored (several GPUs need the periodic spectral configuration)" << std::endl;
+        if (plbm_create(&cfg, &ctx_)) raise("LBmethod: device state");
+        if (plbm_initialize(ctx_)) { plbm_destroy(ctx_); ctx_ = nullptr; raise("LBmethod: Initialize"); }
+    }
     const size_t n = static_cast<size_t>(NX) * NY;
     for (auto& f : fields_) f.assign(n, 0.0);
 }
@@ -45,11 +56,18 @@ LBmethod::LBmethod(const int _NSTEPS, const int _NX, const int _NY, const size_t
 LBmethod::~LBmethod()
 {
     if (ctx_) plbm_fetch_wait(ctx_);
+    if (group_) plbm_group_fetch_wait(group_);
     if (pinned_) {
         for (auto& f : fields_) plbm_unpin_host(f.data());
         for (auto& f : inflight_) plbm_unpin_host(f.data());
     }
     plbm_destroy(ctx_);
+    plbm_group_destroy(group_);
+}
+
+int LBmethod::step_(int nsteps, int want_fields)
+{
+    return group_ ? plbm_group_step(group_, nsteps, want_fields) : plbm_step(ctx_, nsteps, want_fields);
 }
 
 // Run_simulation hands every step's 15 fields to the visualiser: the copy of step t+1 runs on the library's copy
@@ -58,11 +76,11 @@ void LBmethod::begin_fetch()
 {
     double* out[PLBM_NUM_FIELDS] = {};
     for (int k = 0; k < 15; ++k) out[k] = inflight_[k].data();
-    if (plbm_fetch_begin(ctx_, out)) raise("LBmethod: field fetch");
+    if (group_ ? plbm_group_fetch_begin(group_, out) : plbm_fetch_begin(ctx_, out)) raise("LBmethod: field fetch");
 }
 void LBmethod::finish_fetch()
 {
-    if (plbm_fetch_wait(ctx_)) raise("LBmethod: field fetch");
+    if (group_ ? plbm_group_fetch_wait(group_) : plbm_fetch_wait(ctx_)) raise("LBmethod: field fetch");
     for (int k = 0; k < 15; ++k) fields_[k].swap(inflight_[k]);
 }
 
@@ -70,7 +88,7 @@ void LBmethod::fetch_fields()
 {
     double* out[PLBM_NUM_FIELDS] = {};
     for (int k = 0; k < 15; ++k) out[k] = fields_[k].data();
-    if (plbm_download_fields(ctx_, out)) raise("LBmethod: field download");
+    if (group_ ? plbm_group_download_fields(group_, out) : plbm_download_fields(ctx_, out)) raise("LBmethod: field download");
 }
 
 void LBmethod::FetchPotential(std::vector<double>& phi) const
@@ -78,14 +96,14 @@ void LBmethod::FetchPotential(std::vector<double>& phi) const
     phi.resize(static_cast<size_t>(NX) * NY);
     double* out[PLBM_NUM_FIELDS] = {};
     out[PLBM_F_PHI] = phi.data();
-    if (plbm_download_fields(ctx_, out)) raise("LBmethod: potential download");
+    if (group_ ? plbm_group_download_fields(group_, out) : plbm_download_fields(ctx_, out)) raise("LBmethod: potential download");
 }
 
 void LBmethod::Step(int nsteps, bool want_fields)
 {
-    if (plbm_step(ctx_, nsteps, want_fields ? 1 : 0)) raise("LBmethod: time step");
+    if (step_(nsteps, want_fields ? 1 : 0)) raise("LBmethod: time step");
     if (want_fields) fetch_fields();
-    else if (plbm_sync(ctx_)) raise("LBmethod: sync");
+    else if (group_ ? plbm_group_sync(group_) : plbm_sync(ctx_)) raise("LBmethod: sync");
 }
 
 void LBmethod::Run_simulation()
@@ -99,13 +117,13 @@ void LBmethod::Run_simulation()
         for (auto& f : inflight_) pinned_ = pinned_ && plbm_pin_host(f.data(), bytes) == 0;
     }
     if (NSTEPS > 0) {
-        if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+        if (step_(1, 1)) raise("LBmethod: time step");
         begin_fetch();
     }
     for (int t = 0; t < NSTEPS; ++t) {
         finish_fetch();                                       // fields_ = step t
         if (t + 1 < NSTEPS) {
-            if (plbm_step(ctx_, 1, 1)) raise("LBmethod: time step");
+            if (step_(1, 1)) raise("LBmethod: time step");
             begin_fetch();
         }
         visualize::UpdateVisualization(t, NX, NY,
@@ -122,6 +140,7 @@ void LBmethod::Run_simulation()
 
 void LBmethod::Run_simulation_frames()
 {
+    if (group_) throw std::runtime_error("LBmethod::Run_simulation_frames: not available with PLBM_DEVICES (use Run_simulation)");
     if (!visualize::UpdateVisualizationFrames)
         throw std::runtime_error("LBmethod::Run_simulation_frames: the linked visualiser does not implement visualize::UpdateVisualizationFrames");
     visualize::InitVisualization(NX, NY, NSTEPS);

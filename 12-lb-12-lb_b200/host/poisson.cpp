@@ -1,8 +1,9 @@
 // poisson.cpp -- poisson::SolvePoisson and friends with the reference's signatures
 // (include/poisson.hpp) over a process-global, fields-only plbm_ctx.  The reference keeps phi and
 // its FFTW plans in file statics initialised by std::call_once (src/poisson.cpp:9-23, 34-41,
-// 373-376); the same holds here for the device context, so the lattice size and solver type of the
-// first call are the ones that stick, exactly as in the reference.
+// 373-376): the lattice size of the first call is the one that sticks, and so it is here for the
+// device context.  Solver type, boundary type and omega are arguments of EVERY call in the
+// reference (src/poisson.cpp:25-82) and are handed to the context per call (plbm_host_poisson_config).
 #include "poisson.hpp"
 #include "plbm.h"
 
@@ -38,13 +39,14 @@ plbm_ctx* context(int NX, int NY, PoissonType type, streaming::BCType bc, double
         std::atexit(destroy_ctx);                               // reference src/poisson.cpp:375
     });
     if (!g_ctx) throw std::runtime_error("poisson: device state unavailable");
+    if (plbm_host_poisson_config(g_ctx, static_cast<int>(type), static_cast<int>(bc), omega)) raise("poisson: solver selection");
     return g_ctx;
 }
 
-void solver(const std::vector<double>& rho_q, int NX, int NY, PoissonType type, double omega, const char* what)
+void solver(const std::vector<double>& rho_q, int NX, int NY, PoissonType type, double omega, const char* what, int code = -1)
 {
     plbm_ctx* c = context(NX, NY, type, streaming::BCType::Periodic, omega);
-    if (plbm_host_poisson_solver(c, static_cast<int>(type), rho_q.data())) raise(what);
+    if (plbm_host_poisson_solver(c, code >= 0 ? code : static_cast<int>(type), rho_q.data())) raise(what);
 }
 
 } // namespace
@@ -61,11 +63,11 @@ void SolvePoisson_SOR(const std::vector<double>& rho_q, const int NX, const int 
 void SolvePoisson_FFT(const std::vector<double>& rho_q, const int NX, const int NY) { solver(rho_q, NX, NY, PoissonType::FFT, 0.0, "poisson::SolvePoisson_FFT"); }
 void SolvePoisson_9point(const std::vector<double>& rho_q, const int NX, const int NY) { solver(rho_q, NX, NY, PoissonType::NPS, 0.0, "poisson::SolvePoisson_9point"); }
 
-// The *_Periodic solvers are dead code in the reference (never called, src/poisson.cpp:146-211,
-// 283-354, 487-546); they are declared for source compatibility and refuse to run.
-void SolvePoisson_GS_Periodic(const std::vector<double>&, const int, const int) { throw std::runtime_error("poisson::SolvePoisson_GS_Periodic: unused by the reference, not provided"); }
-void SolvePoisson_SOR_Periodic(const std::vector<double>&, const int, const int, const double) { throw std::runtime_error("poisson::SolvePoisson_SOR_Periodic: unused by the reference, not provided"); }
-void SolvePoisson_9point_Periodic(const std::vector<double>&, const int, const int) { throw std::runtime_error("poisson::SolvePoisson_9point_Periodic: unused by the reference, not provided"); }
+// The *_Periodic solvers (reference src/poisson.cpp:146-211, 283-354, 487-546) are never called by the reference's own loop
+// (its Periodic branch runs the Dirichlet solvers, :48-56) but they are public: same sweeps over all cells with wrapped neighbours.
+void SolvePoisson_GS_Periodic(const std::vector<double>& rho_q, const int NX, const int NY) { solver(rho_q, NX, NY, PoissonType::GS, 0.0, "poisson::SolvePoisson_GS_Periodic", PLBM_POISSON_GS_PERIODIC); }
+void SolvePoisson_SOR_Periodic(const std::vector<double>& rho_q, const int NX, const int NY, const double omega) { solver(rho_q, NX, NY, PoissonType::SOR, omega, "poisson::SolvePoisson_SOR_Periodic", PLBM_POISSON_SOR_PERIODIC); }
+void SolvePoisson_9point_Periodic(const std::vector<double>& rho_q, const int NX, const int NY) { solver(rho_q, NX, NY, PoissonType::NPS, 0.0, "poisson::SolvePoisson_9point_Periodic", PLBM_POISSON_NPS_PERIODIC); }
 
 void ComputeElectricField(std::vector<double>& Ex, std::vector<double>& Ey, const int NX, const int NY)
 {

@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (tuning sweeps only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong_8192 / weak_4096 configurations")
     ap.add_argument("--parity-steps", type=int, default=8, help="time steps of the parity gate")
     return ap.parse_args()
 
@@ -214,7 +215,7 @@ def reference_arm(args):
     arm_nx = args.nx or (WEAK_SIDES.get(world, 2048) if world > 1 else 2048)      # the lattice the b200 arm runs at this N
     nx = min(arm_nx, 2048)      # bounded sample: the reference keeps ~2.15 kB of host memory per cell (81 GB at 6144^2)
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, args.cpu_steps * 3))
+    steps = max(1, min(args.steps, 32))        # ~1 s per 2048^2 step on 16 host threads: the driver's K (20) is honoured as it is
     warm = 1 if args.warmup > 0 else 0
     if warm:
         run_cpu_reference(min(nx, 256), 2, args.poisson, threads)
@@ -228,7 +229,8 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "MLUPS (all species)", "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": info.get("loop_s", wall) / steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{arm_nx}x{arm_nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic"},
+            "config": {"workload": workload_name(arm_nx, args.poisson, world),
+                       "sample_lattice": f"{nx}x{nx}" + ("" if nx == arm_nx else " (bounded sample of the workload: MLUPS is per cell update)")},
             "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -299,6 +301,11 @@ def main():
     line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, k1_ms, t["ms_k1"] / ms_total)
     line["clocks"] = clocks.summary()
     line["gpu_launches"] = t["launches"]
+
+    # ---- the lattices BASELINE.json states its scaling targets on, single-GPU points of those curves ----
+    if not args.no_extra:
+        line["strong_8192"] = single_extra(P, args, local_rank, 8192, "8192x8192 strong scaling (BASELINE.json configs[3])", peak)
+        line["weak_4096"] = single_extra(P, args, local_rank, 4096, "4096x4096 = 4096^2 cells per GPU, weak scaling (BASELINE.json configs[4])", peak)
 
     # ---- parity gate: the timed workload against the host checker ---------------------------
     if not args.no_parity:
@@ -388,6 +395,26 @@ def main():
         raise SystemExit("bench.py: the timed path is NOT bit-identical to the host checker (see the line's parity object)")
 
 
+def single_extra(P, args, device, nx, label, peak):
+    """One more lattice on this GPU: 3 untimed + 12 timed steps from the initial condition, device time from the library's events."""
+    K, W = 12, 3
+    try:
+        sim = P.PlasmaLBM(nx, nx, poisson=args.poisson, device=device)
+    except P.PlbmError as e:
+        return {"workload": label, "unavailable": str(e)[:200]}
+    sim.step(W)
+    sim.sync()
+    sim.initialize()
+    seg = sim.step_timed(K)
+    sim.sync()
+    sim.close()
+    cells = nx * nx
+    k1_ms = seg["ms_k1"] / K
+    return {"workload": label, "value": cells * K / (seg["ms_total"] * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": seg["ms_total"] / K,
+            "steps": K, "warmup": W, "k1_ms": k1_ms, "k1_frac_of_hbm_peak": K1_BYTES_PER_UPDATE * cells / (k1_ms * 1e-3) / 1e9 / peak,
+            "poisson_ms": seg["ms_poisson"] / K}
+
+
 SEGMENT = 48
 
 
@@ -413,13 +440,18 @@ E2E_WHAT = ("plbm_upload_state of the 6 AoS population arrays from pinned host m
 WEAK_SIDES = {1: 2048, 2: 3072, 4: 4096, 8: 6144}
 
 
+def workload_name(nx, poisson, world):
+    """The same string in both arms, so that the driver can tell they ran the same configuration."""
+    cfg = "BASELINE.json configs[2]" if world == 1 else "BASELINE.json configs[4]-style weak scaling, 2048^2 cells per GPU"
+    return f"{nx}x{nx} plasma D2Q9 3 species + DDF thermal, {poisson.upper()} Poisson, periodic ({cfg})"
+
+
 def base_line(args, nx, world, K, W, ms_total, mlups, cfg_name):
     cells = nx * nx
     return {"metric": "MLUPS (all species)", "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{nx}x{nx} plasma D2Q9 3 species + DDF thermal, {args.poisson.upper()} Poisson, periodic "
-                                   f"(BASELINE.json {cfg_name})",
+            "config": {"workload": workload_name(nx, args.poisson, world),
                        "initial_condition": "reference Initialize(): e/i block in the central square, neutrals uniform; restarted every "
                                             f"{SEGMENT} timed steps (restart inside the timed region) because the reference's dynamics overflow "
                                             "to NaN after ~85 steps at this size on the CPU as well",
@@ -438,8 +470,11 @@ def roofline(nx, cells, achieved, peak, peak_src, k1_ms, share):
                 traffic = rec.get("dram_bytes_per_launch")
         except Exception:
             pass
-    return {"bound": "hbm", "kernel": "k1_fused_kernel<false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": share}
+    return {"bound": "hbm", "kernel": "k1_fused_kernel<false,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": ("committed ncu capture (profiles/k1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch), "
+                               "not measured in this run" if traffic is not None else None),
+            "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": share}
 
 
 def parity_multi(args, P, torch, dist, world, rank, local_rank):
@@ -478,45 +513,97 @@ def parity_multi(args, P, torch, dist, world, rank, local_rank):
             "mismatches": int(flag.item()), "cases": report, "bar": "bit-identical (sign of zero aside)", "checker": checker}
 
 
-def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
-    """Slab decomposition over `world` GPUs: halo send/recv + two all-to-alls per step (NCCL)."""
-    import torch.distributed as dist
-    nx = args.nx or WEAK_SIDES.get(world) or (int(2048 * world ** 0.5) // 64 * 64)
-    parity = None if args.no_parity else parity_multi(args, P, torch, dist, world, rank, local_rank)
-    sampler = ClockSampler(local_rank).start()
+def timed_slabs(args, P, torch, dist, world, rank, local_rank, nx, K, W, sampler=None):
+    """One timed run of nx x nx on `world` y-slabs: W untimed steps, then K steps (restarted from the initial condition every
+    SEGMENT steps) between barriers; device time by CUDA events on the library's stream, max over ranks.  Returns a dict with the
+    whole-job MLUPS, ms per step, K1's time per launch, the per-stage device times of the slowest-K1 rank and the open driver."""
     b = P.CudaSlabBackend(nx, nx, rank, world, poisson=args.poisson, device=local_rank)
     drv = P.SlabDriver(b)
     drv.step(min(W, SEGMENT))
     b.sync(); torch.cuda.synchronize(); dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_events = []
-    with sampler as clocks:
+    k1_events, stage_ms = [], {}
+
+    def timed_region():
         with b.stream_context():
             ev0.record()
         for n in segments(K):
             b.sim.initialize()
             drv.refresh_halos()
-            drv.step(n, timing=k1_events)
+            if drv.peer:
+                drv.step(n, stage_ms=stage_ms)
+            else:
+                drv.step(n, timing=k1_events)
         with b.stream_context():
             ev1.record()
         b.sync(); torch.cuda.synchronize()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=f"cuda:{local_rank}")
+
+    if sampler is not None:
+        with sampler:
+            timed_region()
+    else:
+        timed_region()
+    dev = f"cuda:{local_rank}"
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    k1 = torch.tensor([sum(a.elapsed_time(c) for a, c in k1_events) / max(len(k1_events), 1)], dtype=torch.float64, device=f"cuda:{local_rank}")
-    dist.all_reduce(k1, op=dist.ReduceOp.MAX)
-    ms_total, k1_ms = float(ms.item()), float(k1.item())
+    if drv.peer:
+        timed = max(stage_ms.get("timed_steps", 0), 1)
+        mine = [stage_ms.get(n, 0.0) / timed for n in b.STAGES]
+    else:
+        mine = [sum(a.elapsed_time(c) for a, c in k1_events) / max(len(k1_events), 1)] + [0.0] * 8
+    st = torch.tensor(mine, dtype=torch.float64, device=dev)
+    dist.all_reduce(st, op=dist.ReduceOp.MAX)              # per stage: the slowest rank
+    ms_total = float(ms.item())
     cells = nx * nx
-    local_cells = nx * (b.slab_y0[rank + 1] - b.slab_y0[rank])
-    mlups = cells * K / (ms_total * 1e-3) / 1e6
-    line = base_line(args, nx, world, K, W, ms_total, mlups, "configs[4]-style weak scaling, 2048^2 cells per GPU")
-    achieved = K1_BYTES_PER_UPDATE * local_cells / (k1_ms * 1e-3) / 1e9
-    line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, k1_ms, k1_ms * K / ms_total)
+    out = {"nx": nx, "ms_total": ms_total, "value": cells * K / (ms_total * 1e-3) / 1e6, "ms_per_step": ms_total / K,
+           "k1_ms": float(st[0].item()), "local_cells": nx * (b.slab_y0[rank + 1] - b.slab_y0[rank]), "peer": bool(drv.peer),
+           "stage_us": ({n: round(float(st[k].item()) * 1e3, 1) for k, n in enumerate(b.STAGES)} if drv.peer else None),
+           "drv": drv, "b": b}
+    return out
+
+
+def extra_config(args, P, torch, dist, world, rank, local_rank, nx, label, peak):
+    """A second lattice on the same ranks (BASELINE.json configs[3] / configs[4]): fewer steps, same timing rules."""
+    K, W = 12, 3
+    try:
+        r = timed_slabs(args, P, torch, dist, world, rank, local_rank, nx, K, W)
+    except P.PlbmError as e:
+        return {"workload": label, "unavailable": str(e)[:200]}
+    r["drv"].close(); r["b"].close()
+    ach = K1_BYTES_PER_UPDATE * r["local_cells"] / (r["k1_ms"] * 1e-3) / 1e9
+    return {"workload": label, "value": r["value"], "unit": "MLUPS", "ms_per_step": r["ms_per_step"], "steps": K, "warmup": W,
+            "k1_ms": r["k1_ms"], "k1_frac_of_hbm_peak": ach / peak, "stage_us": r["stage_us"],
+            "transposes": "peer memory" if r["peer"] else "NCCL all-to-all"}
+
+
+# BASELINE.json configs[4]: weak scaling at 4096^2 cells per GPU on square lattices of side ~ sqrt(N) (build/weak_scalability.py);
+# sides 2^a 3^b 5^c keep the spectral solve on the register passes: 4096, 5760 = 2^7*45, 8192, 11520 = 2^8*45
+WEAK4096_SIDES = {1: 4096, 2: 5760, 4: 8192, 8: 11520}
+
+
+def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
+    """Slab decomposition over `world` GPUs: halo rows, the spectral transposes and the phi rows through peer memory (NVLink),
+    or NCCL send/recv + two all-to-alls per step where peer memory is unavailable."""
+    import torch.distributed as dist
+    nx = args.nx or WEAK_SIDES.get(world) or (int(2048 * world ** 0.5) // 64 * 64)
+    parity = None if args.no_parity else parity_multi(args, P, torch, dist, world, rank, local_rank)
+    sampler = ClockSampler(local_rank).start()
+    r = timed_slabs(args, P, torch, dist, world, rank, local_rank, nx, K, W, sampler)
+    drv, b = r["drv"], r["b"]
+    cells = nx * nx
+    line = base_line(args, nx, world, K, W, r["ms_total"], r["value"], "configs[4]-style weak scaling, 2048^2 cells per GPU")
+    achieved = K1_BYTES_PER_UPDATE * r["local_cells"] / (r["k1_ms"] * 1e-3) / 1e9
+    line["roofline"] = roofline(nx, cells, achieved, peak, peak_src, r["k1_ms"], r["k1_ms"] * K / r["ms_total"])
     line["roofline"]["note"] = "per GPU (slowest rank)"
-    transposes = ("column pass of the spectral solve reads/writes every slab's half spectrum in place through peer memory (NVLink), 2 flag barriers"
+    if r["stage_us"]:
+        line["stage_us"] = r["stage_us"]
+    transposes = ("column pass of the spectral solve reads/writes every slab's half spectrum in place through peer memory (NVLink), 3 flag barriers"
                   if drv.peer else "2 all-to-all transposes of the half spectrum (NCCL)")
-    line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side (send/recv) + {transposes} + 1 phi row per side"
-    line["clocks"] = clocks.summary()
-    line["gpu_launches"] = K * (9 if drv.peer else 6)      # K1, halo pack/push, P1, P2, P3, unpack (+ 3 barrier kernels with peer memory)
+    line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side + {transposes} + 1 phi row per side"
+    line["clocks"] = sampler.summary()
+    # launches inside the timed region, counted from the sequence the library issues per step (plbm_step_peer: K1, halo push, P1,
+    # barrier, unpack, P2, barrier, P3, barrier) plus the 5 of every restart; without peer memory K1, pack, P1, P2, P3, unpack
+    line["gpu_launches"] = K * (9 if drv.peer else 6) + 5 * len(segments(K))
     if parity is not None:
         line["parity"] = parity
     if not args.no_e2e:
@@ -541,16 +628,38 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": cells * Ke / float(dt.item()) / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": NF * cells * 8, "steps": Ke,
-                       "what": "initial state built on the device (plbm_initialize); per step the time step + download of every slab's 15 "
-                               "visualised fields into pinned host memory (all ranks in parallel)"}
+                       "what": "initial state built on the device (plbm_initialize, as LBmethod's constructor does); per step the time step + "
+                               "download of every slab's 15 visualised fields into pinned host memory (all ranks in parallel; the copy of step t "
+                               "overlaps the kernels of step t+1)",
+                       "host_topology": host_topology()}
+        del out_host
     drv.close()
     b.close()
+    if not args.no_extra:
+        # the configurations BASELINE.json states its scaling targets on, on the same ranks in the same run
+        line["strong_8192"] = extra_config(args, P, torch, dist, world, rank, local_rank, 8192,
+                                           "8192x8192 strong scaling (BASELINE.json configs[3])", peak)
+        wk = WEAK4096_SIDES.get(world)
+        if wk:
+            line["weak_4096"] = extra_config(args, P, torch, dist, world, rank, local_rank, wk,
+                                             f"{wk}x{wk} = 4096^2 cells per GPU, weak scaling (BASELINE.json configs[4])", peak)
     if rank == 0:
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if parity is not None and parity["mismatches"]:
         raise SystemExit("bench.py: the slab-decomposed path is NOT bit-identical to the host checker (see the line's parity object)")
+
+
+def host_topology():
+    """Where the host side of the copies runs: NUMA nodes and CPU count (the per-GPU D2H rate at N > 1 depends on it)."""
+    info = {"cpus": os.cpu_count()}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["numa_nodes"] = len(nodes)
+    except OSError:
+        info["numa_nodes"] = None
+    return info
 
 
 if __name__ == "__main__":

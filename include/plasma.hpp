@@ -18,11 +18,14 @@
 #include <vector>
 
 struct plbm_ctx;
+struct plbm_group;
 
 class LBmethod {
 public:
     // Same parameter list as the reference (include/plasma.hpp:34-49).  n_cores is accepted and
-    // ignored: there is no OpenMP path.  Throws std::runtime_error when no CUDA device is present
+    // ignored: there is no OpenMP path.  With PLBM_DEVICES=N (2..16) in the environment the lattice is cut into N y-slabs on
+    // the GPUs 0..N-1 of the box (periodic boundaries + spectral Poisson only; anything else keeps one GPU) -- main_plasma.cpp
+    // does not change.  Throws std::runtime_error when no CUDA device is present
     // or the configuration is not available on the device.
     LBmethod(const int NSTEPS, const int NX, const int NY, const size_t n_cores,
              const int Z_ion, const int A_ion,
@@ -50,7 +53,9 @@ public:
 private:
     const int NSTEPS, NX, NY;
     const size_t n_cores;
-    plbm_ctx* ctx_ = nullptr;
+    plbm_ctx* ctx_ = nullptr;                                 // one GPU ...
+    plbm_group* group_ = nullptr;                             // ... or, with PLBM_DEVICES=N in the environment, N GPUs (y-slabs, include/plbm.h)
+    int step_(int nsteps, int want_fields);
     std::vector<double> fields_[15];                          // order of visualize::UpdateVisualization
     std::vector<double> inflight_[15];                        // Run_simulation: the step being copied while fields_ is drawn
     bool pinned_ = false;

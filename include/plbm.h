@@ -161,6 +161,15 @@ int plbm_host_solve_poisson(plbm_ctx* ctx, const double* rho_q, double* Ex, doub
 /* the two halves separately: poisson::SolvePoisson_{GS,SOR,FFT,9point} (rho_q -> phi, kept in the context) and
  * poisson::ComputeElectricField[_Periodic] (phi -> Ex, Ey; Ex/Ey are in-out because walls copy onto the rim) */
 int plbm_host_poisson_solver(plbm_ctx* ctx, int poisson_type, const double* rho_q);
+/* The reference passes type, boundary and omega to poisson::SolvePoisson on EVERY call (src/poisson.cpp:25-82; only phi's size and
+ * the NONE zero-fill are call_once): a fields-only context takes the values for its next plbm_host_* calls from here.  omega_sor is
+ * also what plbm_host_poisson_solver(PLBM_POISSON_SOR[_PERIODIC]) uses.  The spectral plan is built on the first FFT request. */
+int plbm_host_poisson_config(plbm_ctx* ctx, int poisson_type, int bc_type, double omega_sor);
+/* additional solver codes for plbm_host_poisson_solver only: poisson::SolvePoisson_{GS,SOR,9point}_Periodic
+ * (reference src/poisson.cpp:146-211, 283-354, 487-546; public in include/poisson.hpp:55-97, not called by the reference's own loop) */
+#define PLBM_POISSON_GS_PERIODIC  5
+#define PLBM_POISSON_SOR_PERIODIC 6
+#define PLBM_POISSON_NPS_PERIODIC 7
 int plbm_host_efield(plbm_ctx* ctx, int bc_type, double* Ex, double* Ey);
 
 /* ---------------------------------------------------------------------------------------------
@@ -220,6 +229,33 @@ int plbm_halo_push(plbm_ctx* ctx);
 int plbm_phi_rows_push(plbm_ctx* ctx);
 /* Unmap the peers' memory.  Every rank must have detached (host-level barrier) before any rank destroys its context. */
 int plbm_peer_detach(plbm_ctx* ctx);
+/* The whole peer-memory step sequence above, nsteps times, in ONE call (no host round trip per kernel).  stage_ms, if not
+ * NULL, must hold 9 floats and receives the accumulated device time [ms] of K1, halo push, P1, barrier, halo unpack, P2,
+ * barrier, P3 + phi rows, barrier (at most the last 32 steps are timed). */
+int plbm_step_peer(plbm_ctx* ctx, int nsteps, int want_fields, float* stage_ms);
+/* Slabs that live in one process: wire the peers from the sibling contexts themselves (cudaDeviceEnablePeerAccess, no IPC).
+ * plbm_peer_prepare_local on every slab first, then plbm_peer_attach_local(ctx, all) with all[s] = context of slab s. */
+int plbm_peer_prepare_local(plbm_ctx* ctx);
+int plbm_peer_attach_local(plbm_ctx* ctx, plbm_ctx* const* all);
+
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs behind ONE host object (the reference's host code is one C++ program: LBmethod with PLBM_DEVICES=N uses this).
+ * A group owns one context per device (slab s on device first_device + s), wires them through peer memory and drives each
+ * from its own host thread; the data path between the slabs is the kernels' own (NVLink), the host only starts the step
+ * sequences.  Field arrays are full-lattice host arrays [NY][NX]; every slab copies its own rows.  Periodic boundaries with the
+ * spectral (or no) Poisson solve, as for any multi-slab run.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct plbm_group plbm_group;
+int plbm_group_create(const plbm_config* cfg /* global lattice; cfg->device = first device or -1 for 0 */, int ndevices, plbm_group** out);
+void plbm_group_destroy(plbm_group* g);
+int plbm_group_size(const plbm_group* g);
+plbm_ctx* plbm_group_member(plbm_group* g, int slab);
+int plbm_group_initialize(plbm_group* g);
+int plbm_group_step(plbm_group* g, int nsteps, int want_fields);
+int plbm_group_sync(plbm_group* g);
+int plbm_group_download_fields(plbm_group* g, double* const out[PLBM_NUM_FIELDS]);
+int plbm_group_fetch_begin(plbm_group* g, double* const out[PLBM_NUM_FIELDS]);
+int plbm_group_fetch_wait(plbm_group* g);
 
 /* Self-test hook: the library's fast division primitives on caller-supplied operands.
  * mode 0: a[i] / b[i] (data-dependent divisor); mode 1: a[i] / b[0] through the two-term 1/b[0] product (b[0] in {3,5,6});

@@ -37,7 +37,8 @@ int main(int argc, char** argv)
     int Z_ion = 1, A_ion = 1;
     double n_e = 1e11, n_n = 1e18, T_e = 1e4, T_i = 300, T_n = 300, Ex_SI = 1e-2, Ey_SI = 0.0, omega = 1.8;
     bool phases = false, pops = false;
-    std::string out, dump;
+    int periodic_solver = 0, calls = 1;          // --periodic-solver 1|2|4: call poisson::SolvePoisson_{GS,SOR,9point}_Periodic directly
+    std::string out, dump, rhoq_path;
     for (int i = 1; i < argc; ++i) {
         auto is = [&](const char* k) { return std::strcmp(argv[i], k) == 0; };
         auto next = [&]() { if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", argv[i]); std::exit(2); } return argv[++i]; };
@@ -61,6 +62,9 @@ int main(int argc, char** argv)
         else if (is("--dump")) dump = next();
         else if (is("--pops")) pops = true;
         else if (is("--phases")) phases = true;
+        else if (is("--periodic-solver")) periodic_solver = std::atoi(next());
+        else if (is("--calls")) calls = std::atoi(next());
+        else if (is("--rhoq")) rhoq_path = next();
         else { std::fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
     }
     ref_hook::Config& hook = ref_hook::config();
@@ -78,6 +82,31 @@ int main(int argc, char** argv)
     }
     const auto ptype = static_cast<poisson::PoissonType>(poisson_i);
     const auto btype = static_cast<streaming::BCType>(bc_i);
+
+    if (periodic_solver) {
+        // The *_Periodic solvers (src/poisson.cpp:146-211, 283-354, 487-546) are public but never called by the reference's own
+        // loop.  They work on the file-static phi, which only poisson::SolvePoisson sizes (call_once, :34-41): one call with
+        // PoissonType::NONE does that (and zeroes E), then the solver under test runs `calls` times on rho_q read from --rhoq
+        // (warm start, like successive time steps).  phi after the last call goes to <out>/phi_periodic.f64.
+        omp_set_num_threads(threads);
+        std::vector<double> rho_q((size_t)NX * NY), Ex((size_t)NX * NY), Ey((size_t)NX * NY);
+        FILE* fr = std::fopen(rhoq_path.c_str(), "rb");
+        if (!fr || std::fread(rho_q.data(), sizeof(double), rho_q.size(), fr) != rho_q.size()) { std::perror("--rhoq"); return 1; }
+        std::fclose(fr);
+        poisson::SolvePoisson(Ex, Ey, rho_q, NX, NY, omega, poisson::PoissonType::NONE, streaming::BCType::Periodic);
+        for (int k = 0; k < calls; ++k) {
+            if (periodic_solver == 1) poisson::SolvePoisson_GS_Periodic(rho_q, NX, NY);
+            else if (periodic_solver == 2) poisson::SolvePoisson_SOR_Periodic(rho_q, NX, NY, omega);
+            else poisson::SolvePoisson_9point_Periodic(rho_q, NX, NY);
+        }
+        const std::string name = out + "/phi_periodic.f64";
+        FILE* fp = std::fopen(name.c_str(), "wb");
+        if (!fp) { std::perror(name.c_str()); return 1; }
+        write_vec(fp, poisson::oracle_phi());
+        std::fclose(fp);
+        std::printf("{\"periodic_solver\": %d, \"calls\": %d, \"nx\": %d, \"ny\": %d}\n", periodic_solver, calls, NX, NY);
+        return 0;
+    }
 
     const double t0 = now_s();
     LBmethod lb(NSTEPS, NX, NY, static_cast<size_t>(threads), Z_ion, A_ion, Ex_SI, Ey_SI, T_e, T_i, T_n, n_e, n_n,

@@ -29,8 +29,44 @@ SMALL = [  # name, NX, NY, steps, poisson, bc, dump steps
 POINTS_200 = [(100, 100), (50, 50), (150, 50), (50, 150), (150, 150), (100, 60), (100, 140), (60, 100), (140, 100), (3, 7)]
 
 
+PERIODIC_SOLVERS = [  # name, harness code, NX, NY, calls, omega -- even sizes: with an odd extent cells of one colour are neighbours
+    ("n32x24_gs_periodic_solver", 1, 32, 24, 2, 0.0),          # across the wrap and the reference's own OpenMP sweep is order-dependent
+    ("n32x24_sor_periodic_solver", 2, 32, 24, 2, 1.8),
+    ("n32x24_nps_periodic_solver", 4, 32, 24, 2, 0.0),
+]
+
+
+def periodic_rho_q(NX, NY):
+    """Deterministic zero-mean right-hand side for the periodic solvers (no RNG: the same array anywhere)."""
+    y, x = np.mgrid[0:NY, 0:NX]
+    r = 1e-3 * (np.sin(2 * np.pi * x / NX) * np.cos(4 * np.pi * y / NY) + 0.5 * np.cos(6 * np.pi * x / NX + 2 * np.pi * y / NY))
+    r[NY // 3, NX // 2] += 2e-3
+    r[2 * NY // 3, NX // 4] -= 2e-3
+    return np.ascontiguousarray(r - r.mean())
+
+
+def periodic_solvers():
+    """poisson::SolvePoisson_{GS,SOR,9point}_Periodic of the unmodified reference (never called by its own loop): phi after
+    `calls` warm-started calls on a fixed rho_q, through the harness mode --periodic-solver."""
+    import subprocess, tempfile
+    for name, code, NX, NY, calls, omega in PERIODIC_SOLVERS:
+        rho_q = periodic_rho_q(NX, NY)
+        with tempfile.TemporaryDirectory(prefix="plbm_ref_") as tmp:
+            rho_q.tofile(f"{tmp}/rhoq.f64")
+            subprocess.run([str(O.ref_binary("parity")), "--nx", str(NX), "--ny", str(NY), "--threads", "2", "--omega", repr(omega),
+                            "--periodic-solver", str(code), "--calls", str(calls), "--rhoq", f"{tmp}/rhoq.f64", "--out", tmp], check=True,
+                           capture_output=True)
+            phi = np.fromfile(f"{tmp}/phi_periodic.f64", dtype=np.float64).reshape(NY, NX)
+        np.savez_compressed(HERE / f"{name}.npz", NX=NX, NY=NY, calls=calls, omega=omega, solver=code, rho_q=rho_q, phi=phi)
+        print("wrote", name, "max|phi| =", np.abs(phi).max())
+
+
 def main():
     O.build(ref=True)
+    if "--periodic-solvers-only" in sys.argv:
+        periodic_solvers()
+        return
+    periodic_solvers()
     for name, NX, NY, steps, poisson, bc, dumps in SMALL:
         info, fields, pops = O.run_reference(NX, NY, steps, poisson=poisson, bc=bc, threads=2, dump_steps=dumps, pops=True)
         out = {"NX": NX, "NY": NY, "steps": steps, "poisson": poisson, "bc": bc, "dump_steps": np.array(dumps)}

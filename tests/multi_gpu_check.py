@@ -45,6 +45,36 @@ def main():
                   f"{'peer memory' if drv.peer else 'all-to-all'}: {'ok' if not bad else 'FAILED'}", flush=True)
         drv.close()
         b.close()
+    # an uploaded (not initialised) state on slabs: every rank uploads its rows of one global random state; the halo rows come
+    # from the upload itself and refresh_halos() must leave them alone (it used to overwrite them with stale rows)
+    for peer in (None, False):
+        NX, steps = 96, 3
+        rng = np.random.default_rng(4321)
+        f = rng.uniform(0.05, 1.0, size=(3, NX, NX, 9)); g = rng.uniform(0.01, 0.5, size=(3, NX, NX, 9))
+        f[1] *= 1800.0; f[2] *= 1e9
+        b = P.CudaSlabBackend(NX, NX, rank, world, poisson="fft", device=local, initialize=False)
+        drv = P.SlabDriver(b, peer_memory=(True if (require_peer and peer is None) else peer))
+        y0, y1 = b.slab_y0[rank], b.slab_y0[rank + 1]
+        b.sim.upload_state(f[:, y0:y1], g[:, y0:y1])
+        units = O.units_from_si()
+        b.sim.set_efield(np.full((y1 - y0, NX), units.Ex_ext), np.full((y1 - y0, NX), units.Ey_ext))
+        drv.refresh_halos()
+        drv.step(steps, want_fields=True)
+        b.sync()
+        full = drv.gather_fields(P.FIELD_NAMES)
+        if rank == 0:
+            o = O.PortOracle(NX, NX, poisson="fft", initialize=False)
+            for s in range(3):
+                o.f(s)[...] = f[s]; o.g(s)[...] = g[s]
+            o.scalar(O.PO_EX)[...] = o.units.Ex_ext; o.scalar(O.PO_EY)[...] = o.units.Ey_ext
+            o.step(steps)
+            want = o.fields()
+            nb = sum(not O.same_bits(full[n], want[n]) for n in P.FIELD_NAMES)
+            bad += nb
+            print(f"checked uploaded state {NX}x{NX}/fft, {steps} steps on {world} GPUs, transposes through "
+                  f"{'peer memory' if drv.peer else 'all-to-all'}: {'ok' if not nb else 'FAILED'}", flush=True)
+        drv.close()
+        b.close()
     flag = torch.tensor([bad], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -43,9 +43,9 @@ def test_lbmethod_fails_loudly_without_gpu(plbm):
     assert r.returncode == 1 and "no CUDA device" in r.stderr
 
 
-def run_driver(exe, args, dump_steps, NX, NY, cwd=None):
+def run_driver(exe, args, dump_steps, NX, NY, cwd=None, extra_env=None):
     with tempfile.TemporaryDirectory(prefix="plbm_cpp_") as tmp:
-        env = dict(os.environ, PLBM_DUMP_DIR=tmp, PLBM_DUMP_STEPS=",".join(map(str, dump_steps)))
+        env = dict(os.environ, PLBM_DUMP_DIR=tmp, PLBM_DUMP_STEPS=",".join(map(str, dump_steps)), **(extra_env or {}))
         r = subprocess.run([str(exe)] + [str(a) for a in args], capture_output=True, text=True, env=env, cwd=cwd or tmp)
         assert r.returncode == 0, r.stderr
         out = {}
@@ -147,3 +147,53 @@ def test_unchanged_reference_main_on_the_gpu_library():
             assert_same_bits(np.array([v[y, x] for (x, y) in pts]), z[f"t{t}_{n}_points"], f"{n} points at step {t}")
             stats = np.array([v.sum(), v.min(), v.max(), np.abs(v).sum()])
             assert_same_bits(stats, z[f"t{t}_{n}_stats"], f"{n} stats at step {t}")
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+def test_unchanged_reference_main_on_several_gpus():
+    """The same unchanged src/main_plasma.cpp with PLBM_DEVICES=N in the environment: LBmethod cuts the 200x200 lattice into N
+    y-slabs on N GPUs of the box (one process, one host thread per device, peer memory between the slabs) and still reproduces
+    the golden vectors of the CPU reference bit for bit.  Needs >= 2 GPUs."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    exe = BUILD / "reference_main"
+    if not exe.exists():
+        pytest.skip("reference_main was not built (needs /root/reference at build time)")
+    z = np.load(ROOT / "tests" / "golden" / "n200_fft_periodic_default.npz")
+    dumps = [int(t) for t in z["dump_steps"]]
+    pts = [tuple(p) for p in z["points"]]
+    for ndev in sorted({2, min(n, 8)}):
+        with tempfile.TemporaryDirectory(prefix="plbm_main_") as cwd:
+            os.makedirs(os.path.join(cwd, "build"))
+            got = run_driver(exe, [1], dumps, 200, 200, cwd=cwd, extra_env={"PLBM_DEVICES": str(ndev)})
+        for t in dumps:
+            for name in NAMES15:
+                v = got[t][name]
+                assert_same_bits(np.array([v[y, x] for (x, y) in pts]), z[f"t{t}_{name}_points"], f"{ndev} GPUs: {name} points at step {t}")
+                stats = np.array([v.sum(), v.min(), v.max(), np.abs(v).sum()])
+                assert_same_bits(stats, z[f"t{t}_{name}_stats"], f"{ndev} GPUs: {name} stats at step {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("NX,NY,steps", [(64, 64, 12), (96, 50, 6)])
+def test_lbmethod_on_several_gpus(oracle, NX, NY, steps):
+    """LBmethod::Run_simulation with PLBM_DEVICES=2 (and 4 where present) against the single-domain CPU checker, all 15 fields."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    build_drivers() if not (BUILD / "drive_lbmethod").exists() else None
+    dumps = sorted({0, 1, steps - 1})
+    o = oracle.PortOracle(NX, NY, poisson="fft")
+    want = o.run_with_dumps(steps, dumps)
+    for ndev in sorted({2, min(n, 4)}):
+        got = run_driver(BUILD / "drive_lbmethod", [NX, NY, steps, oracle.POISSON["fft"], oracle.BC["periodic"]], dumps, NX, NY,
+                         extra_env={"PLBM_DEVICES": str(ndev)})
+        for t in dumps:
+            for name in NAMES15:
+                assert_same_bits(got[t][name], want[t][name], f"LBmethod on {ndev} GPUs {NX}x{NY} step {t}: {name}")

@@ -8,7 +8,11 @@ BASELINE.json states, and the only way to hold that tolerance over hundreds of s
 import numpy as np
 import pytest
 
+from pathlib import Path
+
 from helpers import assert_fields_same, assert_same_bits
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
 
 pytestmark = pytest.mark.gpu
 
@@ -63,6 +67,14 @@ def test_benchmark_workload_2048x2048_whole_step(oracle, plbm):
     with plbm.PlasmaLBM(NX, NX, poisson="fft") as sim:
         sim.step(steps, want_fields=True)
         assert_fields_same(sim.fields(), want, f"{NX}x{NX}/fft/t={steps - 1}")
+
+
+@pytest.mark.parametrize("NX,NY", [(64, 64), (50, 70), (129, 33)])
+def test_persistent_warp_kernel_with_tma_pool(oracle, plbm, monkeypatch, NX, NY):
+    """PLBM_K1_POOL=1: K1 as persistent warps whose pulls are done by the TMA engine into a pool of stash buffers
+    (csrc/k1_kernel.cuh: k1_pool_kernel).  Not the default (measured slower), but it must stay bit-identical."""
+    monkeypatch.setenv("PLBM_K1_POOL", "1")
+    run_both(oracle, plbm, NX, NY, "fft", 12, {0, 1, 5, 11})
 
 
 def test_other_physical_parameters(oracle, plbm):
@@ -169,6 +181,39 @@ def test_against_golden_vectors_of_the_unmodified_reference(plbm, name):
     for s in range(3):
         assert_same_bits(f[s], z["pops_f"][s], f"{name}: f[{s}]")
         assert_same_bits(g[s], z["pops_g"][s], f"{name}: g[{s}]")
+
+
+@pytest.mark.parametrize("name,solver", [("n32x24_gs_periodic_solver", "gs_periodic"), ("n32x24_sor_periodic_solver", "sor_periodic"),
+                                         ("n32x24_nps_periodic_solver", "nps_periodic")])
+def test_periodic_iterative_solvers_against_the_unmodified_reference(plbm, name, solver):
+    """poisson::SolvePoisson_{GS,SOR,9point}_Periodic (public in include/poisson.hpp, src/poisson.cpp:146-211, 283-354, 487-546):
+    phi after two warm-started calls on a fixed right-hand side, bit for bit against vectors the unmodified reference produced
+    (tests/golden/make_golden.py: periodic_solvers)."""
+    z = np.load(GOLDEN / f"{name}.npz")
+    NX, NY = int(z["NX"]), int(z["NY"])
+    with plbm.PlasmaLBM(NX, NY, poisson="gs", fields_only=True) as sim:
+        sim.solve_poisson(z["rho_q"] * 0.0)                   # the reference sizes and zeroes phi in its first SolvePoisson call
+        for _ in range(int(z["calls"])):
+            sim.poisson_solver(solver, z["rho_q"], omega=float(z["omega"]))
+        assert_same_bits(sim.fields(["phi"])["phi"], z["phi"], f"{name}: phi")
+
+
+def test_host_poisson_dispatch_is_per_call(plbm):
+    """ADVICE r1: type, boundary and omega are arguments of every poisson:: call in the reference; a fields-only context must not
+    keep the first call's values.  GS then SOR(omega = 1.8) must differ from GS then SOR(omega = 0) (which leaves phi unchanged),
+    and an FFT request on a context created for GS builds its plan on demand."""
+    NX = NY = 32
+    rng = np.random.default_rng(5)
+    rho_q = rng.normal(0, 1e-3, size=(NY, NX))
+    with plbm.PlasmaLBM(NX, NY, poisson="gs", fields_only=True) as sim:
+        sim.poisson_solver("gs", rho_q)
+        after_gs = sim.fields(["phi"])["phi"].copy()
+        sim.poisson_solver("sor", rho_q, omega=1.8)
+        after_sor = sim.fields(["phi"])["phi"].copy()
+        assert not np.array_equal(after_gs, after_sor)
+        sim.poisson_solver("fft", rho_q)
+        after_fft = sim.fields(["phi"])["phi"]
+        assert np.isfinite(after_fft).all() and not np.array_equal(after_fft, after_sor)
 
 
 def test_nan_and_inf_cells(oracle, plbm):
