@@ -16,6 +16,7 @@
 
 #include "exact_math.cuh"
 #include "host_tables.h"
+#include "charge_pull.h"
 #include "k1_fused.h"
 #include "layout.h"
 #include "lbm_consts.h"
@@ -148,6 +149,19 @@ struct plbm_ctx {
     double* down_halo_recv_hi = nullptr;                 // lower neighbour's buffer for what arrives from above
     double* up_phi_below = nullptr;                      // upper neighbour's copy of the row below its slab (= my last row)
     double* down_phi_above = nullptr;
+    // Pipelined peer step (plbm_step_peer): the Poisson solve of step t runs on its own stream beside K1 of step t.  It needs a
+    // second potential (K1 reads phi of step t-1 while P3 writes phi of step t), second copies of the neighbours' boundary rows,
+    // two sets of halo receive buffers (one barrier per exchange instead of three), and its own barrier flags and epoch.
+    cudaStream_t pstream = nullptr;
+    cudaEvent_t ev_pop = nullptr, ev_phi = nullptr;
+    double* rho_q_next = nullptr;                        // charge density pulled from the planes the last step wrote (charge_pull.cu)
+    double* phi_buf[2] = { nullptr, nullptr };           // c->phi == phi_buf[phi_par]
+    double* phi_below_base = nullptr; double* phi_above_base = nullptr;         // [2][NX]; c->phi_below == base + phi_par*NX
+    double* up_phi_below_base = nullptr; double* down_phi_above_base = nullptr; // the neighbours' pairs
+    int phi_par = 0;                                     // which potential is the current one (all slabs flip together)
+    double mass[2] = { 1.0, 1.0 };                        // m_e, m_i (charge_pull.cu)
+    int halo_par = 0;                                    // which halo receive buffers the next exchange uses
+    unsigned long long epoch_b = 0;                      // barriers of the Poisson stream (second half of the flag arrays)
     void* peer_mapped[PEER_NBUF * PLBM_MAX_RANKS] = {};  // bases returned by cudaIpcOpenMemHandle
     int* peer_timeout = nullptr;                         // device flag: a barrier gave up waiting
     unsigned long long epoch = 0;
@@ -185,6 +199,17 @@ struct DevGuard {
     DevGuard(const DevGuard&) = delete;
     DevGuard& operator=(const DevGuard&) = delete;
 };
+
+// Makes potential `par` (and the matching copies of the neighbours' boundary rows, here and in the neighbours) the current one.
+void set_phi_parity(plbm_ctx* c, int par)
+{
+    c->phi_par = par;
+    if (c->phi_buf[par]) c->phi = c->phi_buf[par];
+    const size_t NX = (size_t)c->cfg.NX;
+    if (c->phi_below_base) { c->phi_below = c->phi_below_base + par * NX; c->phi_above = c->phi_above_base + par * NX; }
+    if (c->up_phi_below_base) c->up_phi_below = c->up_phi_below_base + par * NX;
+    if (c->down_phi_above_base) c->down_phi_above = c->down_phi_above_base + par * NX;
+}
 
 template <class T>
 int dev_alloc(plbm_ctx* c, T** p, size_t count)
@@ -491,6 +516,7 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
         c->cfg.y0 = c->slab_y0[c->cfg.rank];
         c->cfg.NY_local = c->slab_y0[c->cfg.rank + 1] - c->cfg.y0;
     }
+    c->mass[0] = cfg->m[0]; c->mass[1] = cfg->m[1];
     c->geom.NX = cfg->NX;
     c->geom.NYl = c->cfg.NY_local;
     c->geom.pitch = ((cfg->NX + 15) / 16) * 16;
@@ -564,11 +590,13 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
     if (c->cfg.nranks > 1) {
         const size_t hn = (size_t)18 * cfg->NX;
         TRY_OR_DESTROY(dev_alloc(c, &c->halo_send_lo, hn)); TRY_OR_DESTROY(dev_alloc(c, &c->halo_send_hi, hn));
-        TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_lo, hn)); TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_hi, hn));
-        TRY_OR_DESTROY(dev_alloc(c, &c->phi_below, (size_t)cfg->NX)); TRY_OR_DESTROY(dev_alloc(c, &c->phi_above, (size_t)cfg->NX));
-        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_below, 0, sizeof(double) * cfg->NX, c->stream));
-        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_above, 0, sizeof(double) * cfg->NX, c->stream));
+        TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_lo, 2 * hn)); TRY_OR_DESTROY(dev_alloc(c, &c->halo_recv_hi, 2 * hn));     // two sets: halo_par
+        TRY_OR_DESTROY(dev_alloc(c, &c->phi_below_base, (size_t)2 * cfg->NX)); TRY_OR_DESTROY(dev_alloc(c, &c->phi_above_base, (size_t)2 * cfg->NX));
+        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_below_base, 0, sizeof(double) * 2 * cfg->NX, c->stream));
+        CUDA_OR_DESTROY(cudaMemsetAsync(c->phi_above_base, 0, sizeof(double) * 2 * cfg->NX, c->stream));
+        c->phi_below = c->phi_below_base; c->phi_above = c->phi_above_base;
     }
+    c->phi_buf[0] = c->phi;
     TRY_OR_DESTROY(build_consts(c));
     if (cfg->poisson_type == PLBM_POISSON_FFT && cfg->bc_type == PLBM_BC_PERIODIC) TRY_OR_DESTROY(build_fft(c));
     CUDA_OR_DESTROY(cudaStreamSynchronize(c->stream));
@@ -585,7 +613,7 @@ void plbm_destroy(plbm_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto e : c->events) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) cudaFree(c->pop[b]);
-    cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi);
+    cudaFree(c->Ex); cudaFree(c->Ey); cudaFree(c->rho_q); cudaFree(c->phi_buf[0] ? c->phi_buf[0] : c->phi);
     for (void* m : c->peer_mapped) if (m) cudaIpcCloseMemHandle(m);
     cudaFree(c->flags); cudaFree(c->peer_timeout);
     for (int b = 0; b < 2; ++b) for (int k = 0; k < 12; ++k) cudaFree(c->macro_sets[b][k]);
@@ -602,7 +630,11 @@ void plbm_destroy(plbm_ctx* c)
     if (c->fft.T2 != c->fft.T1) cudaFree(c->fft.T2);
     cudaFree(c->fft.T1);
     cudaFree(c->halo_send_lo); cudaFree(c->halo_send_hi); cudaFree(c->halo_recv_lo); cudaFree(c->halo_recv_hi);
-    cudaFree(c->phi_below); cudaFree(c->phi_above);
+    cudaFree(c->phi_below_base); cudaFree(c->phi_above_base);
+    cudaFree(c->phi_buf[1]); cudaFree(c->rho_q_next);
+    if (c->pstream) cudaStreamDestroy(c->pstream);
+    if (c->ev_pop) cudaEventDestroy(c->ev_pop);
+    if (c->ev_phi) cudaEventDestroy(c->ev_phi);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -625,6 +657,9 @@ int plbm_initialize(plbm_ctx* c)
         return 0;
     }
     if (!c->pop[0]) return fail("plbm_initialize: context was created with fields_only");
+    if (c->pstream) CUDA_TRY(cudaStreamSynchronize(c->pstream));
+    set_phi_parity(c, 0);          // every slab restarts with the same potential and halo buffers current
+    c->halo_par = 0;
     // the state of a freshly constructed LBmethod (reference src/plasma.cpp:58-124): initial populations,
     // E = E_ext, phi = 0 and the Poisson module's call_once not yet taken
     const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
@@ -1035,7 +1070,8 @@ int plbm_halo_unpack(plbm_ctx* c)
     DevGuard guard__(c);
     if (!c || c->cfg.nranks < 2) return fail("plbm_halo_unpack: needs a multi-slab context");
     if (c->halo_fresh) return 0;            // initialise / upload filled the halo rows: nothing to exchange (see plbm_upload_state)
-    CUDA_TRY(launch_halo_unpack(c->pop[c->cur], c->halo_recv_lo, c->halo_recv_hi, c->geom, c->stream));
+    const size_t hoff = (size_t)c->halo_par * 18 * c->cfg.NX;
+    CUDA_TRY(launch_halo_unpack(c->pop[c->cur], c->halo_recv_lo + hoff, c->halo_recv_hi + hoff, c->geom, c->stream));
     return 0;
 }
 
@@ -1068,12 +1104,28 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
 }
 
 namespace {
+// Second stream, events and buffers of the pipelined peer step, on first use.
+int ensure_pipeline(plbm_ctx* c)
+{
+    if (c->pstream) return 0;
+    const size_t n = (size_t)c->cfg.NX * c->geom.NYl;
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->pstream, cudaStreamNonBlocking, hi));   // its short kernels go first when a slot frees up
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pop, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_phi, cudaEventDisableTiming));
+    if (dev_alloc(c, &c->rho_q_next, n)) return 1;
+    if (dev_alloc(c, &c->phi_buf[1], n)) return 1;
+    CUDA_TRY(cudaMemsetAsync(c->phi_buf[1], 0, sizeof(double) * n, c->stream));
+    return 0;
+}
+
 int ensure_peer_flags(plbm_ctx* c)
 {
     if (c->flags) return 0;
-    if (dev_alloc(c, &c->flags, PLBM_MAX_RANKS)) return 1;
+    if (dev_alloc(c, &c->flags, 2 * PLBM_MAX_RANKS)) return 1;          // [0..MAX): barriers of the main stream, [MAX..2MAX): of the Poisson stream
     if (dev_alloc(c, &c->peer_timeout, 1)) return 1;
-    CUDA_TRY(cudaMemset(c->flags, 0, sizeof(unsigned long long) * PLBM_MAX_RANKS));
+    CUDA_TRY(cudaMemset(c->flags, 0, sizeof(unsigned long long) * 2 * PLBM_MAX_RANKS));
     CUDA_TRY(cudaMemset(c->peer_timeout, 0, sizeof(int)));
     return 0;
 }
@@ -1087,7 +1139,7 @@ int plbm_peer_export(plbm_ctx* c, void* blob)
     if (ensure_peer_flags(c)) return 1;
     PeerBlob b;
     std::memset(&b, 0, sizeof(b));
-    const void* bufs[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below, c->phi_above };
+    const void* bufs[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below_base, c->phi_above_base };
     for (int i = 0; i < PEER_NBUF; ++i) {
         CUDA_TRY(cudaIpcGetMemHandle(&b.handle[i], const_cast<void*>(bufs[i])));
         if (allocation_offset(bufs[i], &b.offset[i])) return 1;
@@ -1111,7 +1163,7 @@ int plbm_peer_attach(plbm_ctx* c, const void* blobs)
         if (b.rank != s || b.nyl != c->slab_y0[s + 1] - c->slab_y0[s]) return fail("plbm_peer_attach: blob %d does not describe slab %d", s, s);
         void* ptr[PEER_NBUF] = {};
         if (s == me) {
-            void* mine[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below, c->phi_above };
+            void* mine[PEER_NBUF] = { c->fft.T1, c->flags, c->halo_recv_lo, c->halo_recv_hi, c->phi_below_base, c->phi_above_base };
             for (int i = 0; i < PEER_NBUF; ++i) ptr[i] = mine[i];
         } else {
             for (int i = 0; i < PEER_NBUF; ++i) {
@@ -1128,9 +1180,10 @@ int plbm_peer_attach(plbm_ctx* c, const void* blobs)
         }
         c->peer_t1.t1[s] = (cpx*)ptr[0];
         c->peer_flags[s] = (unsigned long long*)ptr[1];
-        if (s == up) { c->up_halo_recv_lo = (double*)ptr[2]; c->up_phi_below = (double*)ptr[4]; }
-        if (s == down) { c->down_halo_recv_hi = (double*)ptr[3]; c->down_phi_above = (double*)ptr[5]; }
+        if (s == up) { c->up_halo_recv_lo = (double*)ptr[2]; c->up_phi_below_base = (double*)ptr[4]; }
+        if (s == down) { c->down_halo_recv_hi = (double*)ptr[3]; c->down_phi_above_base = (double*)ptr[5]; }
     }
+    set_phi_parity(c, c->phi_par);
     c->peers = true;
     return 0;
 }
@@ -1158,9 +1211,10 @@ int plbm_peer_attach_local(plbm_ctx* c, plbm_ctx* const* all)
         }
         c->peer_t1.t1[s] = o->fft.T1;
         c->peer_flags[s] = o->flags;
-        if (s == up) { c->up_halo_recv_lo = o->halo_recv_lo; c->up_phi_below = o->phi_below; }
-        if (s == down) { c->down_halo_recv_hi = o->halo_recv_hi; c->down_phi_above = o->phi_above; }
+        if (s == up) { c->up_halo_recv_lo = o->halo_recv_lo; c->up_phi_below_base = o->phi_below_base; }
+        if (s == down) { c->down_halo_recv_hi = o->halo_recv_hi; c->down_phi_above_base = o->phi_above_base; }
     }
+    set_phi_parity(c, c->phi_par);
     c->peers = true;
     return 0;
 }
@@ -1171,50 +1225,142 @@ int plbm_peer_prepare_local(plbm_ctx* c)
     return ensure_peer_flags(c);
 }
 
-// One whole time step of a slab with peers attached, `nsteps` times, in one call:
-//   K1, halo push, P1, BARRIER, halo unpack, P2 over peer memory, BARRIER, P3 + phi rows into the neighbours, BARRIER
-// (the sequence documented in plbm.h).  stage_ms, if given, receives the accumulated device time of the nine stages in that
-// order (CUDA events on the library's stream; at most the last 32 steps are timed).
+namespace {
+
+int peer_barrier_on(plbm_ctx* c, cudaStream_t stream, int set)
+{
+    PeerFlags pf;
+    for (int s = 0; s < PLBM_MAX_RANKS; ++s) pf.f[s] = c->peer_flags[s] ? c->peer_flags[s] + set * PLBM_MAX_RANKS : nullptr;
+    const unsigned long long epoch = set ? ++c->epoch_b : ++c->epoch;
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(pf, c->cfg.rank, c->cfg.nranks, epoch, c->peer_timeout);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Stage times of plbm_step_peer (PLBM_PEER_STAGES slots): CUDA events on the stream the stage runs on.
+struct StageClock {
+    static constexpr int TIMED = 32;
+    float* out;
+    int nsteps, first_timed;
+    std::vector<cudaEvent_t> ev;              // [timed step][slot][begin, end]
+    StageClock(float* o, int n) : out(o), nsteps(n), first_timed(n > TIMED ? n - TIMED : 0)
+    {
+        if (out) ev.assign((size_t)(nsteps - first_timed) * PLBM_PEER_STAGES * 2, nullptr);
+    }
+    ~StageClock() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+    int mark(int t, int slot, int end, cudaStream_t s)
+    {
+        if (!out || t < first_timed) return 0;
+        cudaEvent_t& e = ev[((size_t)(t - first_timed) * PLBM_PEER_STAGES + slot) * 2 + end];
+        if (!e) CUDA_TRY(cudaEventCreate(&e));
+        CUDA_TRY(cudaEventRecord(e, s));
+        return 0;
+    }
+    void collect()
+    {
+        if (!out) return;
+        for (size_t k = 0; k + 1 < ev.size(); k += 2) {
+            float ms = 0.f;
+            if (ev[k] && ev[k + 1] && cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) out[(k / 2) % PLBM_PEER_STAGES] += ms;
+        }
+    }
+};
+enum { ST_K1 = 0, ST_PUSH, ST_HALO_BAR, ST_UNPACK, ST_PHI_WAIT, ST_PULL, ST_P1, ST_BAR1, ST_P2, ST_BAR2, ST_P3, ST_BAR3 };
+
+#define STAGE(slot, stream, call) (clk.mark(t, slot, 0, stream) || (call) || clk.mark(t, slot, 1, stream))
+
+// K1, halo push, P1, BARRIER, halo unpack, P2 over peer memory, BARRIER, P3 + phi rows into the neighbours, BARRIER -- one stream
+// (the sequence documented in plbm.h; PLBM_PEER_PIPELINE=0)
+int step_peer_sequential(plbm_ctx* c, int nsteps, bool want_fields, StageClock& clk)
+{
+    cudaStream_t A = c->stream;
+    int rc = 0;
+    for (int t = 0; t < nsteps && !rc; ++t) {
+        rc = STAGE(ST_K1, A, one_step(c, want_fields && t == nsteps - 1, nullptr))
+          || STAGE(ST_PUSH, A, plbm_halo_push(c))
+          || STAGE(ST_P1, A, plbm_poisson_stage(c, 0))
+          || STAGE(ST_BAR1, A, peer_barrier_on(c, A, 0))
+          || STAGE(ST_UNPACK, A, plbm_halo_unpack(c))
+          || STAGE(ST_P2, A, plbm_poisson_stage(c, 4))
+          || STAGE(ST_BAR2, A, peer_barrier_on(c, A, 0))
+          || STAGE(ST_P3, A, plbm_poisson_stage(c, 5))
+          || STAGE(ST_BAR3, A, peer_barrier_on(c, A, 0))
+          || plbm_poisson_stage(c, 3);
+    }
+    return rc;
+}
+
+// The same step with the Poisson solve OFF the critical path.  rho_q of step t depends only on the populations step t-1 wrote
+// (charge_pull.cu), so phi of step t -- which K1 of step t+1 needs -- can be computed while K1 of step t runs:
+//   stream A:  [pop of t-1 complete] -> K1 t (reads phi t-1) -> halo push -> BARRIER_A -> halo unpack -> wait for phi t -> ...
+//   stream B:  [pop of t-1 complete] -> charge pull -> P1 -> BARRIER_B -> P2 over peer memory -> BARRIER_B -> P3 into the OTHER
+//              potential + boundary rows into the neighbours' other copies -> BARRIER_B -> [phi t ready]
+// Hazards.  K1 t reads potential `par` while P3 t writes `par^1`; the flip happens on every slab after both streams have met.  A
+// neighbour's P3 t+2 overwrites my copies `par` again only after BARRIER_B (2nd of t+2), which I join after my K1 t+1 has
+// finished reading them (stream B of t+2 starts from the event recorded after K1 t+1 and its halo exchange).  The charge pull of t
+// reads the planes K1 t+1 will overwrite; K1 t+1 starts after "phi t ready".  Halo receive buffers alternate (halo_par): the push of
+// t+1 goes into the set the neighbour is not unpacking, the push of t+2 follows BARRIER_A of t+1, which the neighbour joins
+// after its unpack of t.  T1 is reused inside stream B in the order the sequential version already relies on.
+int step_peer_pipelined(plbm_ctx* c, int nsteps, bool want_fields, StageClock& clk)
+{
+    if (ensure_pipeline(c)) return 1;
+    if (poisson_first_call(c)) return 1;
+    cudaStream_t A = c->stream, B = c->pstream;
+    const LbmGeom& g = c->geom;
+    int rc = 0;
+    for (int t = 0; t < nsteps && !rc; ++t) {
+        const int alt = c->phi_par ^ 1;
+        const size_t NX = (size_t)c->cfg.NX;
+        // A -> B: the populations of the previous step are complete, halo rows included
+        CUDA_TRY(cudaEventRecord(c->ev_pop, A));
+        CUDA_TRY(cudaStreamWaitEvent(B, c->ev_pop, 0));
+        rc = STAGE(ST_PULL, B, (launch_charge_pull(c->pop[c->cur], c->rho_q_next, g, c->consts.q, c->mass, B) != cudaSuccess ? fail("charge pull launch failed") : 0))
+          || STAGE(ST_P1, B, (launch_poisson_rows_fwd(c->fft, c->rho_q_next, B) != cudaSuccess ? fail("P1 launch failed") : 0))
+          || STAGE(ST_BAR1, B, peer_barrier_on(c, B, 1))
+          || STAGE(ST_P2, B, (launch_poisson_cols(c->fft, B, &c->peer_t1) != cudaSuccess ? fail("P2 launch failed") : 0))
+          || STAGE(ST_BAR2, B, peer_barrier_on(c, B, 1))
+          || STAGE(ST_P3, B, (launch_poisson_rows_inv(c->fft, c->phi_buf[alt], B, c->down_phi_above_base + alt * NX, c->up_phi_below_base + alt * NX) != cudaSuccess
+                              ? fail("P3 launch failed") : 0))
+          || STAGE(ST_BAR3, B, peer_barrier_on(c, B, 1));
+        if (rc) break;
+        CUDA_TRY(cudaEventRecord(c->ev_phi, B));
+        // A: the step itself, beside all of the above
+        rc = STAGE(ST_K1, A, one_step(c, want_fields && t == nsteps - 1, nullptr))
+          || STAGE(ST_PUSH, A, plbm_halo_push(c))
+          || STAGE(ST_HALO_BAR, A, peer_barrier_on(c, A, 0))
+          || STAGE(ST_UNPACK, A, plbm_halo_unpack(c));
+        if (rc) break;
+        c->halo_par ^= 1;
+        // B -> A: the next K1 (and any download) sees phi of this step; the wait is what is left of the solve on the critical path
+        if (clk.mark(t, ST_PHI_WAIT, 0, A)) return 1;
+        CUDA_TRY(cudaStreamWaitEvent(A, c->ev_phi, 0));
+        if (clk.mark(t, ST_PHI_WAIT, 1, A)) return 1;
+        set_phi_parity(c, alt);
+        c->e_stale = true;
+    }
+    return rc;
+}
+#undef STAGE
+
+} // namespace
+
+// One whole time step of a slab with peers attached, `nsteps` times, in one call (no host round trip per kernel).  Default: the
+// pipelined sequence above; PLBM_PEER_PIPELINE=0 in the environment selects the sequential one.  stage_ms, if given, holds
+// PLBM_PEER_STAGES floats and receives the accumulated device time of each stage over at most the last 32 steps.
 int plbm_step_peer(plbm_ctx* c, int nsteps, int want_fields, float* stage_ms)
 {
     DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_step_peer: peer memory is not attached");
     if (nsteps < 0) return fail("plbm_step_peer: nsteps = %d", nsteps);
-    constexpr int NS = 9, TIMED = 32;
-    std::vector<cudaEvent_t> ev;
-    const int first_timed = nsteps > TIMED ? nsteps - TIMED : 0;
-    if (stage_ms) {
-        ev.resize((size_t)(NS + 1) * (nsteps - first_timed));
-        for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+    const char* e = std::getenv("PLBM_PEER_PIPELINE");
+    const bool pipelined = !(e && e[0] == '0');
+    StageClock clk(stage_ms, nsteps);
+    int rc = pipelined ? step_peer_pipelined(c, nsteps, want_fields != 0, clk) : step_peer_sequential(c, nsteps, want_fields != 0, clk);
+    if (!rc && stage_ms) {
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || (c->pstream && cudaStreamSynchronize(c->pstream) != cudaSuccess))
+            rc = fail("plbm_step_peer: stream synchronisation failed");
+        else clk.collect();
     }
-    auto mark = [&](int t, int k) -> int {
-        if (!stage_ms || t < first_timed) return 0;
-        CUDA_TRY(cudaEventRecord(ev[(size_t)(t - first_timed) * (NS + 1) + k], c->stream));
-        return 0;
-    };
-    int rc = 0;
-    for (int t = 0; t < nsteps && !rc; ++t) {
-        rc = mark(t, 0) || one_step(c, want_fields && t == nsteps - 1, nullptr) || mark(t, 1)
-          || plbm_halo_push(c) || mark(t, 2)
-          || plbm_poisson_stage(c, 0) || mark(t, 3)
-          || plbm_peer_barrier(c) || mark(t, 4)
-          || plbm_halo_unpack(c) || mark(t, 5)
-          || plbm_poisson_stage(c, 4) || mark(t, 6)
-          || plbm_peer_barrier(c) || mark(t, 7)
-          || plbm_poisson_stage(c, 5) || mark(t, 8)
-          || plbm_peer_barrier(c) || mark(t, 9)
-          || plbm_poisson_stage(c, 3);
-    }
-    if (stage_ms && !rc) {
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail("plbm_step_peer: stream synchronisation failed");
-        for (int t = first_timed; t < nsteps && !rc; ++t)
-            for (int k = 0; k < NS; ++k) {
-                float ms = 0.f;
-                const size_t b = (size_t)(t - first_timed) * (NS + 1);
-                if (cudaEventElapsedTime(&ms, ev[b + k], ev[b + k + 1]) == cudaSuccess) stage_ms[k] += ms;
-            }
-    }
-    for (auto& e : ev) cudaEventDestroy(e);
     return rc;
 }
 
@@ -1224,7 +1370,8 @@ int plbm_halo_push(plbm_ctx* c)
     DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_halo_push: peer memory is not attached");
     if (c->halo_fresh) return 0;            // initialise / upload filled the halo rows: nothing to exchange (see plbm_upload_state)
-    CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->down_halo_recv_hi, c->up_halo_recv_lo, c->geom, c->stream));
+    const size_t hoff = (size_t)c->halo_par * 18 * c->cfg.NX;
+    CUDA_TRY(launch_halo_pack(c->pop[c->cur], c->down_halo_recv_hi + hoff, c->up_halo_recv_lo + hoff, c->geom, c->stream));
     return 0;
 }
 int plbm_phi_rows_push(plbm_ctx* c)
@@ -1254,12 +1401,7 @@ int plbm_peer_barrier(plbm_ctx* c)
 {
     DevGuard guard__(c);
     if (!c || !c->peers) return fail("plbm_peer_barrier: peer memory is not attached");
-    PeerFlags pf;
-    for (int s = 0; s < PLBM_MAX_RANKS; ++s) pf.f[s] = c->peer_flags[s];
-    ++c->epoch;
-    peer_barrier_kernel<<<1, 32, 0, c->stream>>>(pf, c->cfg.rank, c->cfg.nranks, c->epoch, c->peer_timeout);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return peer_barrier_on(c, c->stream, 0);
 }
 
 int plbm_peer_check(plbm_ctx* c)

@@ -121,12 +121,15 @@ class CudaSlabBackend:
     def halo_push(self):
         _check(self.lib, self.lib.plbm_halo_push(self.sim._h), "plbm_halo_push")
 
-    STAGES = ("k1", "halo_push", "p1_rows_fwd", "barrier1", "halo_unpack", "p2_cols_peer", "barrier2", "p3_rows_inv_phi_rows", "barrier3")
+    # plbm.h: PLBM_PEER_STAGES; main stream: k1 .. phi_wait, Poisson stream: charge_pull .. barrier3
+    STAGES = ("k1", "halo_push", "halo_barrier", "halo_unpack", "phi_wait", "charge_pull", "p1_rows_fwd", "barrier1", "p2_cols_peer",
+              "barrier2", "p3_rows_inv_phi_rows", "barrier3")
 
     def step_peer(self, nsteps: int, want_fields: bool = False, stage_ms=None):
-        """The whole peer-memory step sequence nsteps times in one library call (plbm_step_peer).  stage_ms: a dict that
-        receives the accumulated device time [ms] of the nine stages (STAGES; at most the last 32 steps are timed)."""
-        buf = (C.c_float * 9)() if stage_ms is not None else None
+        """The whole peer-memory step sequence nsteps times in one library call (plbm_step_peer; by default with the Poisson
+        solve of a step on a second stream beside its K1).  stage_ms: a dict that receives the accumulated device time [ms] of
+        the stages (STAGES; at most the last 32 steps are timed)."""
+        buf = (C.c_float * len(self.STAGES))() if stage_ms is not None else None
         _check(self.lib, self.lib.plbm_step_peer(self.sim._h, nsteps, int(want_fields), buf), "plbm_step_peer")
         if stage_ms is not None:
             for k, name in enumerate(self.STAGES):
