@@ -845,15 +845,15 @@ int plbm_fetch_begin(plbm_ctx* c, double* const out[PLBM_NUM_FIELDS])
     if (c->fetch_pending) return fail("plbm_fetch_begin: the previous fetch was not completed with plbm_fetch_wait");
     if ((out[PLBM_F_EX] || out[PLBM_F_EY]) && materialise_efield(c)) return 1;
     const size_t n = (size_t)c->geom.NX * c->geom.NYl, bytes = sizeof(double) * n;
-    if (!c->copy_stream) {                                 // first use: second macro set, snapshot buffers, copy stream
-        CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
-        for (int k = 0; k < 4; ++k) if (dev_alloc(c, &c->snap[k], n)) return 1;
-        if (!c->unfused && !c->cfg.fields_only) {
-            c->macro_cur = 0;
-            for (int k = 0; k < 12; ++k) if (dev_alloc(c, &c->macro_sets[1][k], n)) return 1;
-        }
+    // first use: copy stream and events (plbm_frames_begin may have created them already), snapshot buffers, second macro set --
+    // each guarded by its own pointer, so that a context that mixes plbm_frames_begin and plbm_fetch_begin has them all
+    if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->ev_snap) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming));
+    if (!c->ev_fetched) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fetched, cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) if (!c->snap[k] && dev_alloc(c, &c->snap[k], n)) return 1;
+    if (!c->unfused && !c->cfg.fields_only && !c->macro_sets[1][0]) {
+        // the set the pending copy reads must not be the one the next step writes: from now on the steps alternate
+        for (int k = 0; k < 12; ++k) if (dev_alloc(c, &c->macro_sets[1][k], n)) return 1;
     }
     bool any_macro = false;
     for (int k = 0; k < 12; ++k) any_macro |= (out[k] != nullptr);
@@ -1270,7 +1270,7 @@ enum { ST_K1 = 0, ST_PUSH, ST_HALO_BAR, ST_UNPACK, ST_PHI_WAIT, ST_PULL, ST_P1, 
 #define STAGE(slot, stream, call) (clk.mark(t, slot, 0, stream) || (call) || clk.mark(t, slot, 1, stream))
 
 // K1, halo push, P1, BARRIER, halo unpack, P2 over peer memory, BARRIER, P3 + phi rows into the neighbours, BARRIER -- one stream
-// (the sequence documented in plbm.h; PLBM_PEER_PIPELINE=0)
+// (the sequence documented in plbm.h; the default)
 int step_peer_sequential(plbm_ctx* c, int nsteps, bool want_fields, StageClock& clk)
 {
     cudaStream_t A = c->stream;
@@ -1345,7 +1345,8 @@ int step_peer_pipelined(plbm_ctx* c, int nsteps, bool want_fields, StageClock& c
 } // namespace
 
 // One whole time step of a slab with peers attached, `nsteps` times, in one call (no host round trip per kernel).  Default: the
-// pipelined sequence above; PLBM_PEER_PIPELINE=0 in the environment selects the sequential one.  stage_ms, if given, holds
+// sequential sequence; PLBM_PEER_PIPELINE=1 in the environment selects the pipelined one (bit-identical; on 2 B200s at 3072^2 it is
+// slower, 1.44 vs 1.32 ms per step: the Poisson kernels take the SMs they run on away from K1, which gets 300 us slower).  stage_ms, if given, holds
 // PLBM_PEER_STAGES floats and receives the accumulated device time of each stage over at most the last 32 steps.
 int plbm_step_peer(plbm_ctx* c, int nsteps, int want_fields, float* stage_ms)
 {
@@ -1353,7 +1354,7 @@ int plbm_step_peer(plbm_ctx* c, int nsteps, int want_fields, float* stage_ms)
     if (!c || !c->peers) return fail("plbm_step_peer: peer memory is not attached");
     if (nsteps < 0) return fail("plbm_step_peer: nsteps = %d", nsteps);
     const char* e = std::getenv("PLBM_PEER_PIPELINE");
-    const bool pipelined = !(e && e[0] == '0');
+    const bool pipelined = (e && e[0] == '1');       // measured slower on 2 B200s (profiles/r2_summary.md): opt-in
     StageClock clk(stage_ms, nsteps);
     int rc = pipelined ? step_peer_pipelined(c, nsteps, want_fields != 0, clk) : step_peer_sequential(c, nsteps, want_fields != 0, clk);
     if (!rc && stage_ms) {

@@ -57,10 +57,7 @@ LBmethod::~LBmethod()
 {
     if (ctx_) plbm_fetch_wait(ctx_);
     if (group_) plbm_group_fetch_wait(group_);
-    if (pinned_) {
-        for (auto& f : fields_) plbm_unpin_host(f.data());
-        for (auto& f : inflight_) plbm_unpin_host(f.data());
-    }
+    for (void* p : pinned_ptrs_) plbm_unpin_host(p);           // exactly what was registered
     plbm_destroy(ctx_);
     plbm_group_destroy(group_);
 }
@@ -109,12 +106,13 @@ void LBmethod::Step(int nsteps, bool want_fields)
 void LBmethod::Run_simulation()
 {
     visualize::InitVisualization(NX, NY, NSTEPS);
-    if (!pinned_) {                                           // page-lock both field sets once (best effort)
+    if (!pinned_) {                                           // page-lock both field sets once (best effort, tracked per buffer)
         const size_t bytes = sizeof(double) * static_cast<size_t>(NX) * NY;
         for (auto& f : inflight_) f.assign(static_cast<size_t>(NX) * NY, 0.0);
         pinned_ = true;
-        for (auto& f : fields_) pinned_ = pinned_ && plbm_pin_host(f.data(), bytes) == 0;
-        for (auto& f : inflight_) pinned_ = pinned_ && plbm_pin_host(f.data(), bytes) == 0;
+        for (auto* set : { fields_, inflight_ })
+            for (int k = 0; k < 15; ++k)
+                if (plbm_pin_host(set[k].data(), bytes) == 0) pinned_ptrs_.push_back(set[k].data());
     }
     if (NSTEPS > 0) {
         if (step_(1, 1)) raise("LBmethod: time step");

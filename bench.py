@@ -597,15 +597,16 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
     line["roofline"]["note"] = "per GPU (slowest rank)"
     if r["stage_us"]:
         line["stage_us"] = r["stage_us"]
-    transposes = ("column pass of the spectral solve reads/writes every slab's half spectrum in place through peer memory (NVLink); the solve of "
-                  "step t runs on a second stream beside K1 of step t (plbm_step_peer)"
+    transposes = ("column pass of the spectral solve reads/writes every slab's half spectrum in place through peer memory (NVLink), 3 flag barriers, "
+                  "the whole sequence issued by one library call per batch of steps (plbm_step_peer)"
                   if drv.peer else "2 all-to-all transposes of the half spectrum (NCCL)")
     line["config"]["decomposition"] = f"{world} y-slabs; per step 18 halo rows per side + {transposes} + 1 phi row per side"
     line["clocks"] = sampler.summary()
-    # launches inside the timed region, counted from the sequence the library issues per step (plbm_step_peer: K1, halo push,
-    # barrier, unpack | charge pull, P1, barrier, P2, barrier, P3, barrier) plus the 5 of every restart; without peer memory K1,
-    # pack, P1, P2, P3, unpack
-    line["gpu_launches"] = K * (11 if drv.peer else 6) + 5 * len(segments(K))
+    # launches inside the timed region, counted from the sequence the library issues per step (plbm_step_peer: K1, halo push, P1,
+    # barrier, unpack, P2, barrier, P3, barrier; pipelined: + charge pull and a fourth barrier) plus the 5 of every restart;
+    # without peer memory K1, pack, P1, P2, P3, unpack
+    pipelined = os.environ.get("PLBM_PEER_PIPELINE", "0") == "1"
+    line["gpu_launches"] = K * ((11 if pipelined else 9) if drv.peer else 6) + 5 * len(segments(K))
     if parity is not None:
         line["parity"] = parity
     if not args.no_e2e:

@@ -58,7 +58,8 @@ private:
     int step_(int nsteps, int want_fields);
     std::vector<double> fields_[15];                          // order of visualize::UpdateVisualization
     std::vector<double> inflight_[15];                        // Run_simulation: the step being copied while fields_ is drawn
-    bool pinned_ = false;
+    bool pinned_ = false;                                     // Run_simulation has tried to page-lock the field sets
+    std::vector<void*> pinned_ptrs_;                          // the buffers that were actually registered
     void begin_fetch();
     void finish_fetch();
     void fetch_fields();

@@ -229,10 +229,10 @@ int plbm_halo_push(plbm_ctx* ctx);
 int plbm_phi_rows_push(plbm_ctx* ctx);
 /* Unmap the peers' memory.  Every rank must have detached (host-level barrier) before any rank destroys its context. */
 int plbm_peer_detach(plbm_ctx* ctx);
-/* A whole time step of a slab with peers attached, nsteps times, in ONE call (no host round trip per kernel).  By default the
- * Poisson solve of step t runs on a second stream BESIDE K1 of step t: rho_q of step t is pulled from the planes step t-1
- * wrote (it does not depend on step t's collision), phi of step t lands in a second potential, and K1 of step t+1 waits for
- * it.  PLBM_PEER_PIPELINE=0 in the environment selects the one-stream sequence documented above.  stage_ms, if not NULL, must hold
+/* A whole time step of a slab with peers attached, nsteps times, in ONE call (no host round trip per kernel): the one-stream
+ * sequence documented above.  With PLBM_PEER_PIPELINE=1 in the environment the Poisson solve of step t runs on a second stream
+ * BESIDE K1 of step t instead: rho_q of step t is pulled from the planes step t-1 wrote (it does not depend on step t's
+ * collision), phi of step t lands in a second potential, and K1 of step t+1 waits for it (bit-identical; measured slower).  stage_ms, if not NULL, must hold
  * PLBM_PEER_STAGES floats and receives the accumulated device time [ms] per stage over at most the last 32 steps:
  *   0 K1   1 halo push   2 halo barrier   3 halo unpack   4 wait for phi (what is left of the solve on the critical path)
  *   5 charge pull   6 P1   7 barrier   8 P2 over peer memory   9 barrier   10 P3 + phi rows   11 barrier

@@ -45,6 +45,26 @@ def main():
                   f"{'peer memory' if drv.peer else 'all-to-all'}: {'ok' if not bad else 'FAILED'}", flush=True)
         drv.close()
         b.close()
+    # the pipelined peer step (Poisson solve of step t on a second stream beside K1 of step t, plbm_step_peer with PLBM_PEER_PIPELINE=1)
+    os.environ["PLBM_PEER_PIPELINE"] = "1"
+    for NX, steps in ((64, 9), (256, 7)):
+        b = P.CudaSlabBackend(NX, NX, rank, world, poisson="fft", device=local)
+        drv = P.SlabDriver(b, peer_memory=(True if require_peer else None))
+        if drv.peer:
+            drv.step(steps - 2)
+            drv.step(2, want_fields=True)
+            b.sync()
+            full = drv.gather_fields(P.FIELD_NAMES)
+            if rank == 0:
+                o = O.PortOracle(NX, NX, poisson="fft")
+                o.step(steps)
+                want = o.fields()
+                nb = sum(not O.same_bits(full[n], want[n]) for n in P.FIELD_NAMES)
+                bad += nb
+                print(f"checked pipelined peer step {NX}x{NX}/fft, {steps} steps on {world} GPUs: {'ok' if not nb else 'FAILED'}", flush=True)
+        drv.close()
+        b.close()
+    os.environ["PLBM_PEER_PIPELINE"] = "0"
     # an uploaded (not initialised) state on slabs: every rank uploads its rows of one global random state; the halo rows come
     # from the upload itself and refresh_halos() must leave them alone (it used to overwrite them with stale rows)
     for peer in (None, False):

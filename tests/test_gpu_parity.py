@@ -152,6 +152,88 @@ def test_tiny_and_huge_values_take_the_exact_fallback(oracle, plbm):
                 assert_same_bits(g3[s], o.g(s), f"extreme g[{s}]")
 
 
+def _one_step_against_checker(oracle, plbm, f, g, Ex, Ey, label, steps=1):
+    NY, NX = Ex.shape
+    o = oracle.PortOracle(NX, NY, poisson="none", initialize=False)
+    for s in range(3):
+        o.f(s)[...] = f[s]
+        o.g(s)[...] = g[s]
+    o.scalar(oracle.PO_EX)[...] = Ex
+    o.scalar(oracle.PO_EY)[...] = Ey
+    with plbm.PlasmaLBM(NX, NY, poisson="none", initialize=False) as sim:
+        sim.upload_state(f, g)
+        sim.set_efield(Ex, Ey)
+        with np.errstate(all="ignore"):
+            for t in range(steps):
+                o.step(1)
+                sim.step(1, want_fields=True)
+                assert_fields_same(sim.fields(), o.fields(), f"{label}/t={t}")
+            f3, g3 = sim.download_state()
+            for s in range(3):
+                assert_same_bits(f3[s], o.f(s), f"{label} f[{s}]")
+                assert_same_bits(g3[s], o.g(s), f"{label} g[{s}]")
+    o.close()
+
+
+def test_values_at_the_edges_of_the_gate(oracle, plbm):
+    """The per-cell gate of K1 (csrc/exact_math.cuh: CellGate; DESIGN.md "K1 gate") accepts the fast divisions when every noted
+    value is inside its bounds.  Columns of cells sit just inside and just outside every bound -- population inputs at 2^-950,
+    field at 2^-400, temperatures at 2^-300, velocities at 2^-240, densities at 2^200, a pair density that cancels to zero --
+    and either way the result must be the checker's, bit for bit (Inf/NaN included)."""
+    NX, NY = 96, 16
+    rng = np.random.default_rng(2024)
+    f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9)); g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
+    f[2] *= 1e9
+    Ex = rng.normal(0, 1e-3, size=(NY, NX)); Ey = rng.normal(0, 1e-3, size=(NY, NX))
+    two = lambda e: np.ldexp(1.0, e)
+    col = iter(range(0, NX, 4))
+    def block():
+        c = next(col); return slice(c, c + 4)
+    for e in (-949, -950, -951, -960, -970, -1000, -1040, -1074):          # one tiny population among normal ones
+        b = block(); f[0][:, b, 3] = two(e) * rng.uniform(1.0, 1.9, size=(NY, 4))
+    for e in (-945, -951, -965, -1030):                                   # a whole species tiny (empty-species branch, divisions by tau)
+        b = block(); f[0][:, b, :] = two(e) * rng.uniform(1.0, 1.9, size=(NY, 4, 9)); g[0][:, b, :] = two(e) * rng.uniform(1.0, 1.9, size=(NY, 4, 9))
+    for e in (-299, -301, -700, -949, -952):                              # temperatures
+        b = block(); g[1][:, b, :] = two(e) * rng.uniform(1.0, 1.9, size=(NY, 4, 9))
+    for e in (-399, -401, -600, -1000):                                   # field
+        b = block(); Ex[:, b] = two(e) * rng.uniform(1.0, 1.9, size=(NY, 4)); Ey[:, b] = -two(e)
+    for e in (-239, -241, -300, -500, -559, -561):                        # velocity = tiny momentum over O(1) density
+        b = block(); f[0][:, b, :] = 0.0; f[0][:, b, 0] = 1.0; f[0][:, b, 1] = two(e); Ex[:, b] = 0.0; Ey[:, b] = 0.0
+    for e in (190, 199, 201, 260, 500):                                   # huge densities
+        b = block(); f[2][:, b, :] *= two(e) / 1e9
+    b = block(); f[1][:, b, :] = -f[0][:, b, :]                           # rho_e + rho_i == 0 exactly: pair density zero
+    b = block(); f[2][:, b, :] = 0.0                                      # neutrals empty: 0/0 in their thermal term (tau_n = 1)
+    _one_step_against_checker(oracle, plbm, f, g, Ex, Ey, "gate edges", steps=2)
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_exponents_everywhere(oracle, plbm, seed):
+    """Fuzz: every one of the 54 populations and both field components of every cell gets an independent magnitude from 2^-1074
+    to 2^+300 (mostly moderate, a few extreme, some exact zeros, some negative): whichever side of the gate a cell lands on, one
+    time step equals the checker's bit for bit."""
+    NX, NY = 128, 64
+    rng = np.random.default_rng(seed)
+    def draw(shape, centre):
+        kind = rng.random(shape)
+        e = np.where(kind < 0.80, rng.integers(centre - 12, centre + 12, shape),
+            np.where(kind < 0.90, rng.integers(-400, 120, shape), rng.integers(-1074, 300, shape)))
+        v = np.ldexp(rng.uniform(1.0, 2.0, shape), e)
+        v = np.where(rng.random(shape) < 0.03, 0.0, v)
+        return np.where(rng.random(shape) < 0.02, -v, v)
+    f = np.stack([draw((NY, NX, 9), -3), draw((NY, NX, 9), 8), draw((NY, NX, 9), 30)])
+    g = np.stack([draw((NY, NX, 9), -3), draw((NY, NX, 9), -6), draw((NY, NX, 9), -6)])
+    # most cells moderate throughout, so that single extreme values meet otherwise ordinary cells
+    calm = rng.random((NY, NX)) < 0.5
+    fm = np.stack([rng.uniform(0.05, 1.0, (NY, NX, 9)), 1800 * rng.uniform(0.05, 1.0, (NY, NX, 9)), 1e9 * rng.uniform(0.05, 1.0, (NY, NX, 9))])
+    one = rng.integers(0, 9, (NY, NX))
+    for s in range(3):
+        keep = np.zeros((NY, NX, 9), bool)
+        keep[np.arange(NY)[:, None], np.arange(NX)[None, :], one] = True      # one extreme direction survives in a calm cell
+        f[s] = np.where(calm[..., None] & ~keep, fm[s], f[s])
+    Ex = draw((NY, NX), -10) * np.where(rng.random((NY, NX)) < 0.5, 1, -1); Ey = draw((NY, NX), -10)
+    _one_step_against_checker(oracle, plbm, f, g, Ex, Ey, f"fuzz seed {seed}")
+
+
 @pytest.mark.parametrize("NX,NY,poisson,bc,nsteps", [
     (24, 24, "sor", "bounceback", 6), (24, 24, "gs", "periodic", 6), (24, 24, "nps", "bounceback", 6),
     (24, 24, "fft", "bounceback", 6), (30, 22, "none", "bounceback", 8), (32, 32, "sor", "periodic", 5),
