@@ -55,6 +55,33 @@ static cudaError_t k1_pool_launch(const CUtensorMap& tmap, const double* src, do
     return cudaGetLastError();
 }
 
+template <bool M, bool P>
+static cudaError_t k1_tma_launch(const CUtensorMap& tmap, const double* src, double* dst, const double* a, const double* b, const double* e,
+                                 double* rho_q, const MacroOut& mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t err = cudaFuncSetAttribute(k1_tma_kernel<M, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_tma_smem_bytes());
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    dim3 grid((g.NX + K1_THREADS - 1) / K1_THREADS, g.NYl);
+    k1_tma_kernel<M, P><<<grid, K1_THREADS, k1_tma_smem_bytes(), stream>>>(tmap, src, dst, a, b, e, rho_q, mo, c, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const double* src, double* dst, const double* Ex, const double* Ey,
+                          const double* phi, const double* below, const double* above, double* rho_q,
+                          const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
+{
+    if (phi) {
+        if (mo) return k1_tma_launch<true, true>(tmap, src, dst, phi, below, above, rho_q, *mo, c, g, stream);
+        return k1_tma_launch<false, true>(tmap, src, dst, phi, below, above, rho_q, MacroOut{}, c, g, stream);
+    }
+    if (mo) return k1_tma_launch<true, false>(tmap, src, dst, Ex, Ey, nullptr, rho_q, *mo, c, g, stream);
+    return k1_tma_launch<false, false>(tmap, src, dst, Ex, Ey, nullptr, rho_q, MacroOut{}, c, g, stream);
+}
+
 cudaError_t launch_k1_pool(const CUtensorMap& tmap, const double* src, double* dst, const double* Ex, const double* Ey,
                            const double* phi, const double* below, const double* above, double* rho_q,
                            const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream)
@@ -85,7 +112,7 @@ int k1_prefetch_rows(int NX, int NYl)
 
 // The population planes as the 4-D tensor [sk 6][direction 9][storage row NYl+2][x NX] of doubles; box = one row segment of a
 // 32-cell tile plus the two cells its +-1 pull offsets need, for the six distributions of one direction (k1_pool_kernel).  cuTensorMapEncodeTiled is taken from the driver at run time (no link-time libcuda).
-cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const LbmGeom& g)
+cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const LbmGeom& g, bool pool)
 {
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -102,7 +129,7 @@ cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const Lb
     const cuuint64_t dims[4] = { (cuuint64_t)g.NX, (cuuint64_t)g.NYl + 2, (cuuint64_t)NQ, (cuuint64_t)(2 * NSPEC) };
     const cuuint64_t strides[3] = { (cuuint64_t)g.pitch * sizeof(double), (cuuint64_t)g.plane * sizeof(double),
                                     (cuuint64_t)g.plane * NQ * sizeof(double) };
-    const cuuint32_t box[4] = { (cuuint32_t)POOL_BOX_W, 1u, 1u, (cuuint32_t)(2 * NSPEC) };
+    const cuuint32_t box[4] = { (cuuint32_t)(pool ? POOL_BOX_W : TMA_BOX_W), 1u, 1u, (cuuint32_t)(2 * NSPEC) };
     const cuuint32_t estr[4] = { 1u, 1u, 1u, 1u };
     int promo = (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = std::getenv("PLBM_TMA_L2PROMO")) promo = std::atoi(e);     // tuning: 0 none, 1 64 B, 2 128 B, 3 256 B

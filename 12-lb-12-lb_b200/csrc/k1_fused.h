@@ -27,7 +27,11 @@ cudaError_t launch_k1_fused_phi(const double* src, double* dst, const double* ph
 // Periodic lattices, persistent warps with a TMA-filled pool of stash buffers (k1_kernel.cuh: k1_pool_kernel).  `tmap` describes
 // the planes of `src` as the 4-D tensor [6][9][NYl + 2][NX]; make_k1_tensor_map builds it (once per population buffer).  E comes
 // from phi when `phi` is given (below/above as in launch_k1_fused_phi), else from the Ex/Ey arrays.
-cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const LbmGeom& g);
+cudaError_t make_k1_tensor_map(CUtensorMap* tmap, const double* planes, const LbmGeom& g, bool pool);   // pool: boxes of k1_pool_kernel, else of k1_tma_kernel
+// one CTA per 64-cell tile as launch_k1_fused_phi, the pull done by the TMA engine (k1_tma_kernel)
+cudaError_t launch_k1_tma(const CUtensorMap& tmap, const double* src, double* dst, const double* Ex, const double* Ey,
+                          const double* phi, const double* below, const double* above, double* rho_q,
+                          const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);
 cudaError_t launch_k1_pool(const CUtensorMap& tmap, const double* src, double* dst, const double* Ex, const double* Ey,
                            const double* phi, const double* below, const double* above, double* rho_q,
                            const MacroOut* mo, const LbmConsts& c, const LbmGeom& g, cudaStream_t stream);

@@ -71,6 +71,16 @@ struct PoolLayout {
     }
 };
 
+// k1_tma_kernel: nine TMA boxes (one per direction) of six rows of K1_THREADS + 2 doubles, same column rule as PoolLayout
+constexpr int TMA_BOX_W = K1_THREADS + 2;
+constexpr int TMA_DIR_STRIDE = ((2 * NSPEC * TMA_BOX_W * 8 + 127) / 128) * 128 / 8;      // doubles between two directions' boxes (128-byte aligned)
+struct TmaLayout {
+    __host__ __device__ static constexpr int slot(int sk, int dir)
+    {
+        return dir * TMA_DIR_STRIDE + sk * TMA_BOX_W + ((dir == 0 || dir == 2 || dir == 4) ? 0 : 1);
+    }
+};
+
 struct K1Out {
     double* __restrict__ dst;     // population planes, already offset to this cell
     long long plane;
@@ -622,6 +632,90 @@ struct PoolHook {
         }
     }
 };
+
+// ---- K1 with the pull done by the TMA engine, one CTA per tile (no persistence) ------------------------------------------------
+// Same tiles, grid and cell code as k1_fused_kernel; the 54 LDG, 54 STS and their address arithmetic are replaced by nine boxes
+// {K1_THREADS + 2, 1, 1, 6} that one thread issues onto one mbarrier (box start x0 - 2 where c_x = +1, else x0: FP64 boxes must start
+// at an even x).  The field is loaded while the boxes are in flight.
+static __host__ __device__ constexpr size_t k1_tma_smem_bytes() { return sizeof(double) * NQ * TMA_DIR_STRIDE + 16; }
+constexpr unsigned TMA_TILE_BYTES = NQ * (2 * NSPEC) * TMA_BOX_W * sizeof(double);
+
+template <bool WRITE_MACRO, bool E_FROM_PHI>
+__global__ void PLBM_K1_BOUNDS
+k1_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ src, double* __restrict__ dst,
+              const double* __restrict__ Exf, const double* __restrict__ Eyf, const double* __restrict__ Ezf,
+              double* __restrict__ rho_q, const __grid_constant__ MacroOut mo,
+              const __grid_constant__ LbmConsts c, const __grid_constant__ LbmGeom g)
+{
+    extern __shared__ __align__(128) double stash_all[];
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(stash_all + NQ * TMA_DIR_STRIDE);
+    const int x0 = blockIdx.x * K1_THREADS;
+    const int x = x0 + threadIdx.x;
+    const int y = blockIdx.y;
+    int rm = y, rp = y + 2;                            // storage rows of y-1 and y+1 (storage row = y + 1)
+    if (g.wrap_y) {
+        if (y == 0) rm = g.NYl;
+        if (y == g.NYl - 1) rp = 1;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, TMA_TILE_BYTES);
+        const int bx[NQ] = { x0, x0 - 2, x0, x0, x0, x0 - 2, x0, x0, x0 - 2 };
+        const int br[NQ] = { y + 1, y + 1, rm, y + 1, rp, rm, rm, rp, rp };
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) tma_load_box4(stash_all + i * TMA_DIR_STRIDE, &tmap, bx[i], br[i], i, 0, bar);
+    }
+#if PLBM_K1_PREFETCH
+    if (g.prefetch_rows > 0 && threadIdx.x >= 1 && threadIdx.x <= NPLANES) {
+        int yp = y + g.prefetch_rows;
+        if (yp >= g.NYl && g.wrap_y) yp -= g.NYl;
+        if (yp < g.NYl) {
+            const int n = min(K1_THREADS, g.pitch - x0);
+            const double* seg = src + (long long)(threadIdx.x - 1) * g.plane + (long long)(yp + 1) * g.pitch + x0;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(seg), "r"(n * 8) : "memory");
+        }
+    }
+#endif
+    __syncthreads();                                   // the barrier's initialisation is visible to the waiting threads
+    if (x >= g.NX) return;
+    const int xm = (x == 0) ? g.NX - 1 : x - 1;
+    const int xp = (x == g.NX - 1) ? 0 : x + 1;
+    const long long cidx = (long long)y * g.NX + x;
+    double Ex, Ey;
+    if constexpr (E_FROM_PHI) field_from_phi(Exf, Eyf, Ezf, x, y, xm, xp, g, Ex, Ey);
+    else { Ex = __ldg(Exf + cidx); Ey = __ldg(Eyf + cidx); }
+    const int r0o = (y + 1) * g.pitch;
+    double* stash = stash_all + threadIdx.x;
+
+    mbar_wait(bar, 0);
+    if (x == 0 || x == g.NX - 1) {
+        // periodic wrap in x: the box delivered zeros for the neighbour outside [0, NX)
+        const int rmo = rm * g.pitch, rpo = rp * g.pitch;
+        #pragma unroll 1
+        for (int sk = 0; sk < 2 * NSPEC; ++sk) {
+            const double* p = src + (long long)(sk * NQ) * g.plane;
+            if (x == 0) {
+                stash[TmaLayout::slot(sk, 1)] = __ldg(p + 1 * g.plane + r0o + xm);
+                stash[TmaLayout::slot(sk, 5)] = __ldg(p + 5 * g.plane + rmo + xm);
+                stash[TmaLayout::slot(sk, 8)] = __ldg(p + 8 * g.plane + rpo + xm);
+            }
+            if (x == g.NX - 1) {
+                stash[TmaLayout::slot(sk, 3)] = __ldg(p + 3 * g.plane + r0o + xp);
+                stash[TmaLayout::slot(sk, 6)] = __ldg(p + 6 * g.plane + rmo + xp);
+                stash[TmaLayout::slot(sk, 7)] = __ldg(p + 7 * g.plane + rpo + xp);
+            }
+        }
+    }
+    K1Out o;
+    o.dst = dst + (long long)r0o + x;
+    o.plane = g.plane;
+    o.rho_q = rho_q + cidx;
+    o.mo = mo;
+    o.cidx = cidx;
+    NoHook hook;
+    k1_cell_checked<WRITE_MACRO, TmaLayout>(stash, Ex, Ey, o, &mo, c, hook);
+}
 
 template <bool WRITE_MACRO, bool E_FROM_PHI>
 __global__ void __launch_bounds__(POOL_THREADS, 1)

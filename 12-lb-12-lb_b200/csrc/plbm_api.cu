@@ -116,7 +116,8 @@ struct plbm_ctx {
     cudaStream_t stream = nullptr;
     double* pop[2] = { nullptr, nullptr };   // ping-pong population planes
     alignas(64) CUtensorMap pop_map[2];      // the same planes as TMA tensors (periodic lattices: the pull of K1 is done by the TMA engine)
-    bool tma = false;
+    bool tma = false;                        // k1_pool_kernel (PLBM_K1_POOL=1)
+    bool tma_tile = false;                   // k1_tma_kernel (PLBM_K1_TMA=1)
     int cur = 0;                             // pop[cur] holds the current post-collision state
     double* Ex = nullptr; double* Ey = nullptr; double* rho_q = nullptr; double* phi = nullptr;
     double* macro[12] = {};                  // ux,uy (e,i,n), T (e,i,n), rho (e,i,n) in plbm.h field order (the set last written)
@@ -436,6 +437,11 @@ int one_step(plbm_ctx* c, bool want_fields, long long* launches)
         CUDA_TRY(launch_k1_pool(c->pop_map[c->cur], c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->e_stale ? c->phi : nullptr,
                                slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr, c->rho_q, want_fields ? &mo : nullptr,
                                c->consts, c->geom, c->stream));
+    } else if (c->tma_tile) {
+        const bool slabs = c->cfg.nranks > 1;
+        CUDA_TRY(launch_k1_tma(c->pop_map[c->cur], c->pop[c->cur], c->pop[c->cur ^ 1], c->Ex, c->Ey, c->e_stale ? c->phi : nullptr,
+                               slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr, c->rho_q, want_fields ? &mo : nullptr,
+                               c->consts, c->geom, c->stream));
     } else if (c->e_stale) {
         const bool slabs = c->cfg.nranks > 1;
         CUDA_TRY(launch_k1_fused_phi(c->pop[c->cur], c->pop[c->cur ^ 1], c->phi, slabs ? c->phi_below : nullptr, slabs ? c->phi_above : nullptr,
@@ -547,7 +553,10 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
         // (profiles/r2_k1_sweeps.md), so it is not the default.
         const char* e = std::getenv("PLBM_K1_POOL");
         c->tma = (e && e[0] == '1');
-        for (int b = 0; b < 2 && c->tma; ++b) CUDA_OR_DESTROY(make_k1_tensor_map(&c->pop_map[b], c->pop[b], c->geom));
+        // PLBM_K1_TMA=1: one CTA per tile as k1_fused_kernel, the pull done by the TMA engine (k1_tma_kernel)
+        const char* e2 = std::getenv("PLBM_K1_TMA");
+        c->tma_tile = !c->tma && (e2 && e2[0] == '1');
+        for (int b = 0; b < 2 && (c->tma || c->tma_tile); ++b) CUDA_OR_DESTROY(make_k1_tensor_map(&c->pop_map[b], c->pop[b], c->geom, c->tma));
     }
     TRY_OR_DESTROY(dev_alloc(c, &c->Ex, n));
     TRY_OR_DESTROY(dev_alloc(c, &c->Ey, n));

@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (tuning sweeps only)")
     ap.add_argument("--no-extra", action="store_true", help="skip the strong_8192 / weak_4096 configurations")
+    ap.add_argument("--weak-sides", default="friendly", choices=["friendly", "literal"],
+                    help="weak_4096 lattice sides: 4096/6144/8192/12288 (default) or the literal roundings 4096/5760/8192/11520")
     ap.add_argument("--parity-steps", type=int, default=8, help="time steps of the parity gate")
     return ap.parse_args()
 
@@ -576,9 +578,12 @@ def extra_config(args, P, torch, dist, world, rank, local_rank, nx, label, peak)
             "transposes": "peer memory" if r["peer"] else "NCCL all-to-all"}
 
 
-# BASELINE.json configs[4]: weak scaling at 4096^2 cells per GPU on square lattices of side ~ sqrt(N) (build/weak_scalability.py);
-# sides 2^a 3^b 5^c keep the spectral solve on the register passes: 4096, 5760 = 2^7*45, 8192, 11520 = 2^8*45
-WEAK4096_SIDES = {1: 4096, 2: 5760, 4: 8192, 8: 11520}
+# BASELINE.json configs[4]: weak scaling at 4096^2 cells per GPU on square lattices of side ~ sqrt(N) (build/weak_scalability.py).
+# Sides 2^k and 3*2^k (as for the headline: 1 or 1.125 x 4096^2 cells per GPU) keep the spectral solve on radix-4/2 passes plus one
+# radix-3 pass.  The literal sqrt(N)*4096 roundings 5760 = 2^7*45 and 11520 = 2^8*45 run and are bit-exact too (--weak-sides literal),
+# but their radix-3/3/5 passes make the solve 2.6x slower per cell (profiles/r2_summary.md: N=8, 11520^2: 5.79 ms/step, 2.1 ms of it Poisson).
+WEAK4096_SIDES = {1: 4096, 2: 6144, 4: 8192, 8: 12288}
+WEAK4096_SIDES_LITERAL = {1: 4096, 2: 5760, 4: 8192, 8: 11520}
 
 
 def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
@@ -642,10 +647,11 @@ def multi_gpu(args, P, torch, world, rank, local_rank, K, W, peak, peak_src):
         # the configurations BASELINE.json states its scaling targets on, on the same ranks in the same run
         line["strong_8192"] = extra_config(args, P, torch, dist, world, rank, local_rank, 8192,
                                            "8192x8192 strong scaling (BASELINE.json configs[3])", peak)
-        wk = WEAK4096_SIDES.get(world)
+        wk = (WEAK4096_SIDES_LITERAL if args.weak_sides == "literal" else WEAK4096_SIDES).get(world)
         if wk:
+            per = wk * wk / world / 4096 ** 2
             line["weak_4096"] = extra_config(args, P, torch, dist, world, rank, local_rank, wk,
-                                             f"{wk}x{wk} = 4096^2 cells per GPU, weak scaling (BASELINE.json configs[4])", peak)
+                                             f"{wk}x{wk} = {per:.3f} x 4096^2 cells per GPU, weak scaling (BASELINE.json configs[4])", peak)
     if rank == 0:
         print(json.dumps(line), flush=True)
     dist.barrier()

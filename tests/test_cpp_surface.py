@@ -34,6 +34,19 @@ def test_cpp_surface_builds(plbm):
         assert (BUILD / "reference_main").exists()
 
 
+def test_reference_renderer_type_checks_against_our_header():
+    """the reference's renderer src/visualize.cpp (OpenCV, out of scope) keeps compiling UNCHANGED against
+    this repo's include/visualize.hpp.  The image has no OpenCV, so the check is g++ -fsyntax-only with declarations of the OpenCV
+    calls the renderer makes (tests/host/opencv_shim, OpenCV's own signatures): every symbol the renderer needs from visualize.hpp
+    (namespace, constants, the three entry points and its helper prototypes) is there with a compatible type."""
+    src = Path("/root/reference/src/visualize.cpp")
+    if not src.exists():
+        pytest.skip("needs /root/reference (only in the build container)")
+    r = subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-fopenmp", f"-I{HOST / 'opencv_shim'}", f"-I{ROOT / 'include'}", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
 def test_lbmethod_fails_loudly_without_gpu(plbm):
     import torch
     if torch.cuda.is_available():

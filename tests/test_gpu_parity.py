@@ -77,6 +77,13 @@ def test_persistent_warp_kernel_with_tma_pool(oracle, plbm, monkeypatch, NX, NY)
     run_both(oracle, plbm, NX, NY, "fft", 12, {0, 1, 5, 11})
 
 
+@pytest.mark.parametrize("NX,NY", [(64, 64), (50, 70), (130, 33)])
+def test_tile_kernel_with_tma_pull(oracle, plbm, monkeypatch, NX, NY):
+    """PLBM_K1_TMA=1: the per-tile kernel whose pull is nine TMA boxes instead of per-thread loads (k1_tma_kernel)."""
+    monkeypatch.setenv("PLBM_K1_TMA", "1")
+    run_both(oracle, plbm, NX, NY, "fft", 12, {0, 1, 5, 11})
+
+
 def test_other_physical_parameters(oracle, plbm):
     run_both(oracle, plbm, 40, 40, "fft", 12, {0, 11}, Z_ion=2, A_ion=4, Ex_SI=3e-2, Ey_SI=-1e-2, T_i_SI=500.0)
 
