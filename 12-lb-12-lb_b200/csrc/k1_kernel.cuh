@@ -666,17 +666,7 @@ k1_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict
         #pragma unroll
         for (int i = 0; i < NQ; ++i) tma_load_box4(stash_all + i * TMA_DIR_STRIDE, &tmap, bx[i], br[i], i, 0, bar);
     }
-#if PLBM_K1_PREFETCH
-    if (g.prefetch_rows > 0 && threadIdx.x >= 1 && threadIdx.x <= NPLANES) {
-        int yp = y + g.prefetch_rows;
-        if (yp >= g.NYl && g.wrap_y) yp -= g.NYl;
-        if (yp < g.NYl) {
-            const int n = min(K1_THREADS, g.pitch - x0);
-            const double* seg = src + (long long)(threadIdx.x - 1) * g.plane + (long long)(yp + 1) * g.pitch + x0;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(seg), "r"(n * 8) : "memory");
-        }
-    }
-#endif
+    // (no L2 prefetch here: with the TMA pull it costs 1 %, profiles/r2_k1_sweeps.md)
     __syncthreads();                                   // the barrier's initialisation is visible to the waiting threads
     if (x >= g.NX) return;
     const int xm = (x == 0) ? g.NX - 1 : x - 1;

@@ -553,9 +553,10 @@ int plbm_create(const plbm_config* cfg, plbm_ctx** out)
         // (profiles/r2_k1_sweeps.md), so it is not the default.
         const char* e = std::getenv("PLBM_K1_POOL");
         c->tma = (e && e[0] == '1');
-        // PLBM_K1_TMA=1: one CTA per tile as k1_fused_kernel, the pull done by the TMA engine (k1_tma_kernel)
+        // default: one CTA per tile, the pull done by the TMA engine (k1_tma_kernel: 0.835 ms at 2048^2 against 0.875 ms for
+        // k1_fused_kernel, in which every thread pulls its own populations; PLBM_K1_TMA=0 selects that one)
         const char* e2 = std::getenv("PLBM_K1_TMA");
-        c->tma_tile = !c->tma && (e2 && e2[0] == '1');
+        c->tma_tile = !c->tma && !(e2 && e2[0] == '0');
         for (int b = 0; b < 2 && (c->tma || c->tma_tile); ++b) CUDA_OR_DESTROY(make_k1_tensor_map(&c->pop_map[b], c->pop[b], c->geom, c->tma));
     }
     TRY_OR_DESTROY(dev_alloc(c, &c->Ex, n));

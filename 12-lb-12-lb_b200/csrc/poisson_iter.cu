@@ -16,6 +16,7 @@
 #include "poisson_iter.h"
 
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -97,6 +98,104 @@ poisson_iter_kernel(double* phi, const double* __restrict__ rho_q, int NX, int N
     if (first_thread && iters_out) *iters_out = iter;
 }
 
+// ---- the same solvers for lattices that fit ONE thread-block cluster's shared memory ----------------------------------------------
+// A solve is thousands of colour sweeps of a few ten thousand cells each, separated by barriers: at the reference's default 200x200
+// the grid-wide barrier of the cooperative kernel above (~2.6 us) is the whole cost (26 ms per solve).  Here one cluster of up to 16
+// CTAs keeps phi and rho_q in shared memory for the entire solve: every CTA owns a band of rows, reads the two rows next to its band
+// from the neighbouring CTAs' shared memory (distributed shared memory), and a sweep ends with the cluster's hardware barrier
+// instead of a grid barrier.  The iteration's largest update is reduced per CTA and exchanged through one slot per CTA that every
+// CTA reads after the last colour's barrier, so all CTAs stop at the same -- the reference's -- iteration.  Same arithmetic, same
+// colour order: bit-identical to the cooperative kernel and to the reference.
+constexpr int CL_THREADS = 512;
+constexpr int CL_MAX_CTAS = 16;
+
+template <int KIND, bool PERIODIC>
+__global__ void __launch_bounds__(CL_THREADS)
+poisson_iter_cluster_kernel(double* __restrict__ phi_g, const double* __restrict__ rho_g, int NX, int NY, double omega, int band,
+                            int* __restrict__ iters_out)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), me = (int)cluster.block_rank();
+    extern __shared__ double cl_smem[];
+    double* phi = cl_smem;                                    // [band][NX]: rows me*band .. of the lattice
+    double* rho = cl_smem + (size_t)band * NX;
+    __shared__ unsigned long long cta_err[2];
+    __shared__ double red[CL_THREADS / 32];
+    const int r0 = me * band, r1 = min(NY, r0 + band);        // this CTA's rows (possibly none)
+    for (int t = threadIdx.x; t < (r1 - r0) * NX; t += CL_THREADS) {
+        phi[t] = phi_g[(size_t)r0 * NX + t];
+        rho[t] = rho_g[(size_t)r0 * NX + t];
+    }
+    if (threadIdx.x < 2) cta_err[threadIdx.x] = 0ull;
+    cluster.sync();
+    // row j of phi wherever it lives in the cluster
+    auto row_of = [&](int j) -> const double* {
+        const int owner = j / band;
+        const double* base = (owner == me) ? phi : cluster.map_shared_rank(phi, owner);
+        return base + (size_t)(j - owner * band) * NX;
+    };
+    constexpr int lo = PERIODIC ? 0 : 1;
+    const int hx = PERIODIC ? NX : NX - 1, hy = PERIODIC ? NY : NY - 1;
+    constexpr int NCOL = (KIND == 2) ? 4 : 2;
+    const int warp = threadIdx.x >> 5, nwarp = CL_THREADS / 32;
+    int iter = 0;
+    for (; iter < ITER_MAX; ++iter) {
+        double local = 0.0;
+        for (int colour = 0; colour < NCOL; ++colour) {
+            // rows of the band over the warps, the cells of the colour in a row over the lanes
+            for (int j = max(r0, lo) + warp; j < min(r1, hy); j += nwarp) {
+                if (KIND == 2 && ((j ^ colour) & 1)) continue;                               // 4 colours: rows of the other parity
+                const int ipar = (KIND == 2) ? (colour >> 1) : ((colour ^ j) & 1);           // parity of i in this row
+                const int i0 = lo + ((lo ^ ipar) & 1);
+                const int jn = PERIODIC ? (j + 1 == NY ? 0 : j + 1) : j + 1, js = PERIODIC ? (j == 0 ? NY - 1 : j - 1) : j - 1;
+                const double* rown = row_of(jn);
+                const double* rows = row_of(js);
+                double* row = phi + (size_t)(j - r0) * NX;
+                const double* rq_row = rho + (size_t)(j - r0) * NX;
+                for (int i = i0 + 2 * (int)(threadIdx.x & 31); i < hx; i += 64) {
+                    const int ie = PERIODIC ? (i + 1 == NX ? 0 : i + 1) : i + 1, iw = PERIODIC ? (i == 0 ? NX - 1 : i - 1) : i - 1;
+                    const double old = row[i];
+                    const double rq = rq_row[i];
+                    double nw;
+                    if (KIND == 2) {
+                        const double so = __dadd_rn(__dadd_rn(__dadd_rn(row[ie], row[iw]), rown[i]), rows[i]);
+                        const double sd = __dadd_rn(__dadd_rn(__dadd_rn(rown[ie], rown[iw]), rows[ie]), rows[iw]);
+                        const double num = __dadd_rn(__dadd_rn(__dmul_rn(4.0, so), sd), __dmul_rn(6.0, rq));
+                        nw = PERIODIC ? __dmul_rn(num, 0.05) : __ddiv_rn(num, 20.0);
+                    } else {
+                        const double nb = __dadd_rn(__dadd_rn(__dadd_rn(row[ie], row[iw]), rown[i]), rows[i]);
+                        const double gs = __dmul_rn(0.25, __dadd_rn(nb, rq));
+                        nw = (KIND == 1) ? __dadd_rn(__dmul_rn(__dsub_rn(1.0, omega), old), __dmul_rn(omega, gs)) : gs;
+                    }
+                    row[i] = nw;
+                    local = fmax(local, fabs(__dsub_rn(nw, old)));
+                }
+            }
+            if (colour == NCOL - 1) {                          // this CTA's largest update of the iteration into its slot
+                local = warp_max(local);
+                if ((threadIdx.x & 31) == 0) red[warp] = local;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double m = 0.0;
+                    for (int w = 0; w < nwarp; ++w) m = fmax(m, red[w]);
+                    cta_err[iter & 1] = (unsigned long long)__double_as_longlong(m);
+                }
+            }
+            cluster.sync();                                    // the next colour (or iteration) reads this colour's updates
+        }
+        // every CTA reads every slot: the same maximum, the same decision (slots alternate, two barriers lie between reuse)
+        double maxErr = 0.0;
+        for (int b = 0; b < C; ++b) {
+            const unsigned long long* slot = cluster.map_shared_rank(cta_err, b) + (iter & 1);
+            maxErr = fmax(maxErr, __longlong_as_double((long long)*(volatile const unsigned long long*)slot));
+        }
+        if (maxErr < ITER_TOL) { ++iter; break; }
+    }
+    cluster.sync();                                            // nobody leaves while a neighbour may still read its rows
+    for (int t = threadIdx.x; t < (r1 - r0) * NX; t += CL_THREADS) phi_g[(size_t)r0 * NX + t] = phi[t];
+    if (me == 0 && threadIdx.x == 0 && iters_out) *iters_out = iter;
+}
+
 // poisson.cpp:556-563: interior central differences
 __global__ void efield_interior_kernel(const double* __restrict__ phi, double* __restrict__ Ex, double* __restrict__ Ey, int NX, int NY)
 {
@@ -125,9 +224,46 @@ __global__ void efield_rim_cols_kernel(double* __restrict__ Ex, double* __restri
     Ex[r + NX - 1] = Ex[r + NX - 2];   Ey[r + NX - 1] = Ey[r + NX - 2];
 }
 
+// The cluster-resident kernel when phi and rho_q fit the shared memory of one cluster (<= 16 CTAs x ~200 KB); cudaErrorNotSupported
+// tells the caller to use the cooperative kernel.  PLBM_ITER_CLUSTER=0 disables it (comparison runs).
+static cudaError_t launch_poisson_cluster(int kind, bool periodic, double* phi, const double* rho_q, int NX, int NY, double omega,
+                                          int* iters_out, cudaStream_t stream)
+{
+    if (const char* e = std::getenv("PLBM_ITER_CLUSTER")) if (e[0] == '0') return cudaErrorNotSupported;
+    // measured at 200x200 on B200 (profiles/r2_summary.md): SOR 18.5 vs 28.8 ms per solve, GS 22.0 vs 30.1 -- but the 4-colour 9-point
+    // sweep, with twice the barriers per iteration, is slower through the 16-CTA cluster barrier (42.8 vs 38.6): it keeps the grid kernel
+    if (kind == 2) return cudaErrorNotSupported;
+    void* fns[2][3] = { { (void*)poisson_iter_cluster_kernel<0, false>, (void*)poisson_iter_cluster_kernel<1, false>, (void*)poisson_iter_cluster_kernel<2, false> },
+                        { (void*)poisson_iter_cluster_kernel<0, true>, (void*)poisson_iter_cluster_kernel<1, true>, (void*)poisson_iter_cluster_kernel<2, true> } };
+    void* fn = fns[periodic ? 1 : 0][kind];
+    const size_t smem_max = 200 * 1024;
+    for (int C = CL_MAX_CTAS; C >= 8; C /= 2) {
+        const int band = (NY + C - 1) / C;
+        const size_t smem = sizeof(double) * 2 * (size_t)band * NX;
+        if (smem > smem_max) continue;
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (C > 8 && (e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+        void* args[] = { &phi, &rho_q, &NX, &NY, &omega, (void*)&band, &iters_out };
+        e = cudaLaunchKernelExC(&cfg, fn, args);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+    }
+    return cudaErrorNotSupported;
+}
+
 cudaError_t launch_poisson_iterative(int kind, bool periodic, double* phi, const double* rho_q, int NX, int NY, double omega,
                                      unsigned long long* err_bits, int* iters_out, cudaStream_t stream)
 {
+    if (launch_poisson_cluster(kind, periodic, phi, rho_q, NX, NY, omega, iters_out, stream) == cudaSuccess) return cudaSuccess;
     void* fns[2][3] = { { (void*)poisson_iter_kernel<0, false>, (void*)poisson_iter_kernel<1, false>, (void*)poisson_iter_kernel<2, false> },
                         { (void*)poisson_iter_kernel<0, true>, (void*)poisson_iter_kernel<1, true>, (void*)poisson_iter_kernel<2, true> } };
     void* fn = fns[periodic ? 1 : 0][kind];

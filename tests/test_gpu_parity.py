@@ -78,9 +78,10 @@ def test_persistent_warp_kernel_with_tma_pool(oracle, plbm, monkeypatch, NX, NY)
 
 
 @pytest.mark.parametrize("NX,NY", [(64, 64), (50, 70), (130, 33)])
-def test_tile_kernel_with_tma_pull(oracle, plbm, monkeypatch, NX, NY):
-    """PLBM_K1_TMA=1: the per-tile kernel whose pull is nine TMA boxes instead of per-thread loads (k1_tma_kernel)."""
-    monkeypatch.setenv("PLBM_K1_TMA", "1")
+def test_tile_kernel_with_per_thread_loads(oracle, plbm, monkeypatch, NX, NY):
+    """PLBM_K1_TMA=0: the per-tile kernel in which every thread pulls its own populations (k1_fused_kernel) instead of the default
+    k1_tma_kernel, whose pull is nine TMA boxes."""
+    monkeypatch.setenv("PLBM_K1_TMA", "0")
     run_both(oracle, plbm, NX, NY, "fft", 12, {0, 1, 5, 11})
 
 
@@ -187,7 +188,7 @@ def test_values_at_the_edges_of_the_gate(oracle, plbm):
     value is inside its bounds.  Columns of cells sit just inside and just outside every bound -- population inputs at 2^-950,
     field at 2^-400, temperatures at 2^-300, velocities at 2^-240, densities at 2^200, a pair density that cancels to zero --
     and either way the result must be the checker's, bit for bit (Inf/NaN included)."""
-    NX, NY = 96, 16
+    NX, NY = 160, 16
     rng = np.random.default_rng(2024)
     f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9)); g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
     f[2] *= 1e9
