@@ -51,6 +51,9 @@ namespace plbm {
 #ifndef PLBM_K1_UNROLL
 #define PLBM_K1_UNROLL 0            // 1: all five axes unrolled (20 % fewer instructions, ~60 KB of code per cell: measured slower)
 #endif
+#ifndef PLBM_K1_SHARE
+#define PLBM_K1_SHARE 1             // 1: k1_tma_kernel computes every pair bracket once per cell and hands it on through the stash
+#endif
 constexpr int K1_THREADS = PLBM_K1_THREADS;
 
 // Where a parked population lives in the stash, relative to the thread's own pointer.
@@ -98,6 +101,23 @@ __device__ __forceinline__ D stash_reload(const double* p)
     return D(v);
 }
 
+// Stash accesses of the collision phase when brackets are handed on through it (SHARE): volatile, so that the compiler keeps
+// the program order between the last read of a population and the bracket stored over it, and re-reads shared memory.
+__device__ __forceinline__ D stash_ld(const double* p) { return D(*reinterpret_cast<const volatile double*>(p)); }
+__device__ __forceinline__ void stash_st(double* p, D v) { *reinterpret_cast<volatile double*>(p) = v.v; }
+
+// Pair brackets handed on between the species (SHARE).  The equilibrium bracket of a pair velocity (u_ei, u_en, u_in) in a
+// direction is the same number for both species of the pair (plasma.cpp:195-304 evaluates it once per species), so the first
+// species of a pair leaves it in a stash slot whose population it has just consumed and the second reads it back:
+//   u_ei: electrons -> slot f_e   (read by ions)        u_en: electrons -> slot g_e   (read by neutrals)
+//   u_in: ions      -> slot f_i   (read by neutrals)
+// 27 brackets per cell are not recomputed (-135 FP64 instructions, +27 STS/LDS).  b[j], j = 1, 2 are the pairs of PAIR_SLOT.
+template <int S, int J> struct SharedBracket {
+    static constexpr bool computed = (S == 0) || (S == 1 && J == 2);            // else: read back
+    // stash distribution (species*2 + kind) that carries the bracket of pair PAIR_SLOT[S][J-1]
+    static constexpr int sk = (PAIR_SLOT[S][J - 1] == 0) ? 0 : (PAIR_SLOT[S][J - 1] == 1 ? 1 : 2);
+};
+
 // c_axis . v for the first direction of a compile-time axis (lbm_cell.cuh: axis_select)            (E1)
 template <int AXIS>
 __device__ __forceinline__ D axis_dot_ct(D vx, D vy)
@@ -110,8 +130,8 @@ __device__ __forceinline__ D axis_dot_ct(D vx, D vy)
 
 // One axis with its direction(s) known at compile time: c.v is a move, an addition or a subtraction, the weight class and the
 // store offsets are constants, and the rest direction's bracket is 1 - K.
-template <int S, int AXIS, class L>
-__device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const double* __restrict__ stash, const CellMacro& m,
+template <int S, int AXIS, class L, bool SHARE = false>
+__device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash, const CellMacro& m,
                                            const D (&vx)[3], const D (&vy)[3], const D (&K)[3], const D (&AB2)[3], D rhoh, D u2,
                                            D uE, const D (&pref3)[3], D Ex, D Ey, const K1Out& o, const LbmConsts& c)
 {
@@ -119,8 +139,17 @@ __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const dou
     constexpr int d0 = (AXIS == 4) ? 0 : (AXIS < 2 ? AXIS + 1 : AXIS + 3);    // first direction of the axis; the opposite is d0 + 2
     const D wr = D(c.w[wclass]) * m.rho[S];
     const D wT = D(c.w[wclass]) * m.T[S];
-    auto finish = [&](const int dir, const D (&b)[3], D force) {
-        const D fv = stash_reload(stash + L::slot(S * 2 + 0, dir)), gv = stash_reload(stash + L::slot(S * 2 + 1, dir));
+    auto finish = [&](const int dir, D (&b)[3], D force) {
+        D fv, gv;
+        if constexpr (SHARE) {
+            fv = stash_ld(stash + L::slot(S * 2 + 0, dir)); gv = stash_ld(stash + L::slot(S * 2 + 1, dir));
+            if constexpr (SharedBracket<S, 1>::computed) stash_st(stash + L::slot(SharedBracket<S, 1>::sk, dir), b[1]);
+            else b[1] = stash_ld(stash + L::slot(SharedBracket<S, 1>::sk, dir));
+            if constexpr (SharedBracket<S, 2>::computed) stash_st(stash + L::slot(SharedBracket<S, 2>::sk, dir), b[2]);
+            else b[2] = stash_ld(stash + L::slot(SharedBracket<S, 2>::sk, dir));
+        } else {
+            fv = stash_reload(stash + L::slot(S * 2 + 0, dir)); gv = stash_reload(stash + L::slot(S * 2 + 1, dir));
+        }
         D fnew, gnew;
         collide_species_dir<S>(dv, fv, gv, b, wr, wT, AB2, rhoh, u2, force, c, fnew, gnew);
         gt.note_output(fnew);
@@ -131,12 +160,14 @@ __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, const dou
     if constexpr (AXIS == 4) {
         // rest direction: c = 0, so c.v = 0, the bracket is ((1 + 0) + 0) - K = 1 - K and the Guo bracket (0 + 0/cs2) - u.E
         D b[3];
-        #pragma unroll
-        for (int j = 0; j < 3; ++j) b[j] = D(1.0) - K[j];
+        b[0] = D(1.0) - K[0];
+        if constexpr (!SHARE || SharedBracket<S, 1>::computed) b[1] = D(1.0) - K[1];
+        if constexpr (!SHARE || SharedBracket<S, 2>::computed) b[2] = D(1.0) - K[2];
         D force = D(0.0);
         if constexpr (S < 2) force = pref3[0] * (D(0.0) - uE);
         finish(d0, b, force);
     } else {
+        static_assert(!SHARE, "the fully unrolled variant does not hand brackets on");
         BracketParts bp[3];
         #pragma unroll
         for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot_ct<AXIS>(vx[j], vy[j]), c);
@@ -164,10 +195,11 @@ struct NoHook {
 
 // The whole cell.  L: stash layout.  `hook.at_axis<s>(axis)` runs at the top of every iteration of the axis loop of species s
 // (the pool kernel asks for its next tile at one of them).
-template <bool WRITE_MACRO, class L, class Hook>
-__device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const double* __restrict__ stash, D Ex, D Ey, const K1Out& o,
-                                              const LbmConsts& c, Hook& hook)
+template <bool WRITE_MACRO, class L, bool SHARE, class Hook>
+__device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                              D Ex, D Ey, const K1Out& o, const LbmConsts& c, Hook& hook)
 {
+    static_assert(!(SHARE && PLBM_K1_UNROLL), "the fully unrolled variant does not hand brackets on");
     // ---- UpdateMacro ------------------------------------------------------------------------
     CellMacro m;
     {
@@ -204,10 +236,12 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
         const D vx[3] = { m.ux[s], m.upx[p0], m.upx[p1] };
         const D vy[3] = { m.uy[s], m.upy[p0], m.upy[p1] };
         const D u2 = vx[0] * vx[0] + vy[0] * vy[0];                           // collisions.cpp:98-100
-        D K[3];                                                               // u2*0.5*invcs2, plasma.cpp:199   (E3)
+        // brackets of the pair velocities this species forms itself (all without SHARE; else see SharedBracket)
+        constexpr bool comp1 = !SHARE || SharedBracket<s, 1>::computed, comp2 = !SHARE || SharedBracket<s, 2>::computed;
+        D K[3] = { D(0.0), D(0.0), D(0.0) };                                  // u2*0.5*invcs2, plasma.cpp:199   (E3)
         K[0] = u2 * D(c.hinvcs2);
-        K[1] = (vx[1] * vx[1] + vy[1] * vy[1]) * D(c.hinvcs2);
-        K[2] = (vx[2] * vx[2] + vy[2] * vy[2]) * D(c.hinvcs2);
+        if constexpr (comp1) K[1] = (vx[1] * vx[1] + vy[1] * vy[1]) * D(c.hinvcs2);
+        if constexpr (comp2) K[2] = (vx[2] * vx[2] + vy[2] * vy[2]) * D(c.hinvcs2);
         D AB2[3];
         thermal_cell_terms<s>(m.rho[s], c, AB2);
         const D rhoh = D(0.5) * m.rho[s];
@@ -233,8 +267,9 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
             const D wr = w * m.rho[s];
             const D wT = w * m.T[s];
             BracketParts bp[3];
-            #pragma unroll
-            for (int j = 0; j < 3; ++j) bp[j] = bracket_parts(axis_dot(sel, vx[j], vy[j]), c);
+            bp[0] = bracket_parts(axis_dot(sel, vx[0], vy[0]), c);
+            if constexpr (comp1) bp[1] = bracket_parts(axis_dot(sel, vx[1], vy[1]), c);
+            if constexpr (comp2) bp[2] = bracket_parts(axis_dot(sel, vx[2], vy[2]), c);
             D pref = D(0.0), X = D(0.0), cE = D(0.0);
             if constexpr (s < 2) {
                 cE = axis_dot(sel, Ex, Ey);
@@ -244,8 +279,16 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
             auto direction = [&](auto NEG, const int dir, const D fv, const D gv) {
                 constexpr bool neg = decltype(NEG)::value;
                 D b[3];
-                #pragma unroll
-                for (int j = 0; j < 3; ++j) b[j] = bracket_value<neg>(bp[j], K[j]);
+                b[0] = bracket_value<neg>(bp[0], K[0]);
+                if constexpr (comp1) b[1] = bracket_value<neg>(bp[1], K[1]);
+                if constexpr (comp2) b[2] = bracket_value<neg>(bp[2], K[2]);
+                if constexpr (SHARE) {
+                    // fv, gv of this direction are in registers: their slots carry the pair brackets from here on
+                    if constexpr (comp1) stash_st(stash + L::slot(SharedBracket<s, 1>::sk, dir), b[1]);
+                    else b[1] = stash_ld(stash + L::slot(SharedBracket<s, 1>::sk, dir));
+                    if constexpr (comp2) stash_st(stash + L::slot(SharedBracket<s, 2>::sk, dir), b[2]);
+                    else b[2] = stash_ld(stash + L::slot(SharedBracket<s, 2>::sk, dir));
+                }
                 D force = D(0.0);
                 if constexpr (s < 2) force = pref * guo_bracket<neg>(X, cE, uE);   // collisions.cpp:154-163
                 D fnew, gnew;
@@ -257,29 +300,28 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, const 
             };
             const int d0 = (axis < 2) ? axis + 1 : axis + 3;                  // first direction of the axis; the opposite is d0 + 2
             // both directions of the axis in one straight-line block: six independent division chains
-            const D f0 = D(stash[L::slot(s * 2 + 0, d0)]), g0 = D(stash[L::slot(s * 2 + 1, d0)]);
-            const D f1 = D(stash[L::slot(s * 2 + 0, d0 + 2)]), g1 = D(stash[L::slot(s * 2 + 1, d0 + 2)]);
+            D f0, g0, f1, g1;
+            if constexpr (SHARE) {
+                f0 = stash_ld(stash + L::slot(s * 2 + 0, d0));     g0 = stash_ld(stash + L::slot(s * 2 + 1, d0));
+                f1 = stash_ld(stash + L::slot(s * 2 + 0, d0 + 2)); g1 = stash_ld(stash + L::slot(s * 2 + 1, d0 + 2));
+            } else {
+                f0 = D(stash[L::slot(s * 2 + 0, d0)]);     g0 = D(stash[L::slot(s * 2 + 1, d0)]);
+                f1 = D(stash[L::slot(s * 2 + 0, d0 + 2)]); g1 = D(stash[L::slot(s * 2 + 1, d0 + 2)]);
+            }
             direction(std::false_type{}, d0, f0, g0);
             direction(std::true_type{}, d0 + 2, f1, g1);
         }
-        k1_axis_ct<s, 4, L>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
+        k1_axis_ct<s, 4, L, SHARE>(dv, gt, stash, m, vx, vy, K, AB2, rhoh, u2, uE, pref3, Ex, Ey, o, c);
 #endif
     });
 }
 
-// Out-of-line recomputation of one cell with the reference's literal arithmetic (literal_cell.cuh): taken when the
-// gate trips (operands outside the fast divisions' domain, non-finite values).
-template <bool WRITE_MACRO, class L>
-static __device__ __noinline__ void k1_cell_literal(const double* stash, double Ex, double Ey, double* dst, long long plane, double* rho_q,
-                                                    const MacroOut* mo, long long cidx, const LbmConsts* c)
+// Recomputation of one cell with the reference's literal arithmetic (literal_cell.cuh): taken when the gate trips (operands
+// outside the fast divisions' domain, non-finite values).  f, g: the cell's 54 pulled populations.
+template <bool WRITE_MACRO>
+static __device__ __forceinline__ void k1_literal_body(const D (&f)[3][NQ], const D (&g)[3][NQ], double Ex, double Ey, double* dst, long long plane,
+                                                       double* rho_q, const MacroOut* mo, long long cidx, const LbmConsts* c)
 {
-    // scalar arguments only (no pointer to the caller's K1Out): the fast path keeps its addresses in registers
-    D f[3][NQ], g[3][NQ];
-    for (int s = 0; s < 3; ++s)
-        for (int i = 0; i < NQ; ++i) {
-            f[s][i] = D(stash[L::slot(s * 2 + 0, i)]);
-            g[s][i] = D(stash[L::slot(s * 2 + 1, i)]);
-        }
     LitMacro m;
     lit_update_macro(f, g, D(Ex), D(Ey), *c, m);
     *rho_q = m.rho_q.v;
@@ -300,6 +342,47 @@ static __device__ __noinline__ void k1_cell_literal(const double* stash, double 
     }
 }
 
+// Out of line, from the populations still parked in the stash.
+template <bool WRITE_MACRO, class L>
+static __device__ __noinline__ void k1_cell_literal(const double* stash, double Ex, double Ey, double* dst, long long plane, double* rho_q,
+                                                    const MacroOut* mo, long long cidx, const LbmConsts* c)
+{
+    // scalar arguments only (no pointer to the caller's K1Out): the fast path keeps its addresses in registers
+    D f[3][NQ], g[3][NQ];
+    for (int s = 0; s < 3; ++s)
+        for (int i = 0; i < NQ; ++i) {
+            f[s][i] = D(stash[L::slot(s * 2 + 0, i)]);
+            g[s][i] = D(stash[L::slot(s * 2 + 1, i)]);
+        }
+    k1_literal_body<WRITE_MACRO>(f, g, Ex, Ey, dst, plane, rho_q, mo, cidx, c);
+}
+
+// Out of line, pulling the populations from the source planes again: the fast path of k1_tma_kernel has overwritten part of the
+// stash with pair brackets (SharedBracket).  One CTA per K1_THREADS-cell tile of a row, as launched by k1_tma_launch.
+template <bool WRITE_MACRO>
+static __device__ __noinline__ void k1_cell_literal_pull(const double* src, const LbmGeom* gp, double Ex, double Ey, double* dst, double* rho_q,
+                                                         const MacroOut* mo, const LbmConsts* c)
+{
+    const LbmGeom& g = *gp;
+    const int x = blockIdx.x * K1_THREADS + threadIdx.x, y = blockIdx.y;
+    const int xm = (x == 0) ? g.NX - 1 : x - 1;
+    const int xp = (x == g.NX - 1) ? 0 : x + 1;
+    int rm = y, rp = y + 2;                            // storage rows of y-1 and y+1
+    if (g.wrap_y) {
+        if (y == 0) rm = g.NYl;
+        if (y == g.NYl - 1) rp = 1;
+    }
+    const long long r0o = (long long)(y + 1) * g.pitch, rmo = (long long)rm * g.pitch, rpo = (long long)rp * g.pitch;
+    const long long off[NQ] = { r0o + x, r0o + xm, rmo + x, r0o + xp, rpo + x, rmo + xm, rmo + xp, rpo + xp, rpo + xm };
+    D f[3][NQ], gg[3][NQ];
+    for (int s = 0; s < 3; ++s)
+        for (int i = 0; i < NQ; ++i) {
+            f[s][i] = D(__ldg(src + (long long)((s * 2 + 0) * NQ + i) * g.plane + off[i]));
+            gg[s][i] = D(__ldg(src + (long long)((s * 2 + 1) * NQ + i) * g.plane + off[i]));
+        }
+    k1_literal_body<WRITE_MACRO>(f, gg, Ex, Ey, dst, g.plane, rho_q, mo, (long long)y * g.NX + x, c);
+}
+
 // Gate, fast path and -- outside the gate -- the literal recomputation of one cell whose populations are parked at `stash`.
 // The fallback is skipped when every population input is zero or NaN and a raw density is NaN (CellGate::all_nan): then all 54
 // outputs are NaN on either path (each species is coupled to both others through the pair velocities) and the moments and
@@ -311,8 +394,20 @@ __device__ __forceinline__ void k1_cell_checked(const double* __restrict__ stash
 {
     CellGate gt;
     GatedDiv dv;
-    k1_cell_gated<WRITE_MACRO, L>(dv, gt, stash, D(Ex), D(Ey), o, c, hook);
-    if (!gt.ok()) k1_cell_literal<WRITE_MACRO, L>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, mo, o.cidx, &c);
+    k1_cell_gated<WRITE_MACRO, L, false>(dv, gt, stash, D(Ex), D(Ey), o, c, hook);
+    if (!gt.ok(dv.ok())) k1_cell_literal<WRITE_MACRO, L>(stash, Ex, Ey, o.dst, o.plane, o.rho_q, mo, o.cidx, &c);
+}
+
+// The same with pair brackets handed on through the stash (k1_tma_kernel): the fallback pulls the cell's populations again.
+template <bool WRITE_MACRO, class L>
+__device__ __forceinline__ void k1_cell_checked_share(double* stash, double Ex, double Ey, const K1Out& o, const MacroOut* mo,
+                                                      const LbmConsts& c, const double* src, const LbmGeom* g)
+{
+    CellGate gt;
+    GatedDiv dv;
+    NoHook hook;
+    k1_cell_gated<WRITE_MACRO, L, true>(dv, gt, stash, D(Ex), D(Ey), o, c, hook);
+    if (!gt.ok(dv.ok())) k1_cell_literal_pull<WRITE_MACRO>(src, g, Ex, Ey, o.dst, o.rho_q, mo, &c);
 }
 
 #ifdef PLBM_K1_MAXNREG
@@ -703,8 +798,12 @@ k1_tma_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict
     o.rho_q = rho_q + cidx;
     o.mo = mo;
     o.cidx = cidx;
+#if PLBM_K1_SHARE
+    k1_cell_checked_share<WRITE_MACRO, TmaLayout>(stash, Ex, Ey, o, &mo, c, src, &g);
+#else
     NoHook hook;
     k1_cell_checked<WRITE_MACRO, TmaLayout>(stash, Ex, Ey, o, &mo, c, hook);
+#endif
 }
 
 template <bool WRITE_MACRO, bool E_FROM_PHI>

@@ -292,8 +292,14 @@ __device__ __forceinline__ void collide_species_dir(DV& dv, D fv, D gv, const D 
         constexpr int tau = TAU_VALUE[slot];
         feq[m] = wr * b[m];                                                   // plasma.cpp:195-249
         geq[m] = wT * b[m];                                                   // plasma.cpp:251-304
-        const D C18 = c18_over_tau<tau>(dv, feq[m], c);                       // 2 * (Q*feq/tau)          (E3)
-        q[m] = dv.xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                    // 2 * term_xy, collisions.cpp:86-96
+        if constexpr (tau == 1 && DV::unit_quotient_shortcut) {
+            // a = 1 - 1/tau = 0: AB2 = a4 = 0 and the quotient below is (0 - C18)/(0 + C18) = -1 (GatedDiv::note_unit_quotient)
+            dv.note_unit_quotient(feq[m]);
+            q[m] = D(-1.0);
+        } else {
+            const D C18 = c18_over_tau<tau>(dv, feq[m], c);                   // 2 * (Q*feq/tau)          (E3)
+            q[m] = dv.xdiv(AB2[m] - C18, D(c.a4[slot]) + C18);                // 2 * term_xy, collisions.cpp:86-96
+        }
         df[m] = div_tau<tau>(dv, fv - feq[m], c);                             // collisions.cpp:166-168
         dg[m] = div_tau<tau>(dv, gv - geq[m], c);                             // collisions.cpp:107-109
     });
