@@ -189,9 +189,82 @@ __device__ __forceinline__ void k1_axis_ct(GatedDiv& dv, CellGate& gt, std::cond
     }
 }
 
+// ---- an EMPTY charged species (stored density 0: raw density below the reference's 1e-10 threshold, plasma.cpp:373-377) ---------
+// With rho_s = 0 the reference's own expressions collapse exactly: u_s = 0 and T_s = 0 (plasma.cpp:373-377), so for every partner m
+//   feq_m = (w*0)*b_m = 0, geq_m = (w*0)*b_m = 0            (b_m finite: the gate bounds all six velocities)
+//   term_m = (0 - 0)/(a4_m + 0) = 0                         (a4_m > 0: electrons and ions have no partner with tau = 1)
+//   DeltaE = (0.5*0 * 0) * 0 = 0, DeltaT = 0/Kb = 0, Guo term = (w q 0/m/cs2 (1 - 1/2tau)) * bracket = 0
+// and what is left of collisions.cpp:107-114,166-173 is  f - ((f/tau_0 + f/tau_1) + f/tau_2)  and the same for g -- 16 FP64
+// instructions per direction instead of ~150.  Bit-identical up to the sign of exact zeros.  In the reference's own initial
+// condition (plasma.cpp:128-158) electrons and ions are empty outside the central quarter of the lattice.  Not for neutrals:
+// their self collision has tau = 1 (a4 = 0), the reference divides 0 by 0 there and the full path reproduces that.
+// With SHARE the species still leaves the pair brackets it owes the later species in the stash.
+#ifndef PLBM_K1_LIGHT
+#define PLBM_K1_LIGHT 1
+#endif
+template <int S, class L, bool SHARE, bool BOTH>   // BOTH: electrons and ions are both empty, nobody reads the bracket of u_ei
+__device__ __forceinline__ void k1_species_empty(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                                 const CellMacro& m, const K1Out& o, const LbmConsts& c)
+{
+    static_assert(S < 2, "neutrals take the full path");
+    constexpr int T0 = TAU_VALUE[TAU_SLOT[S][0]], T1 = TAU_VALUE[TAU_SLOT[S][1]], T2 = TAU_VALUE[TAU_SLOT[S][2]];
+    static_assert(T0 != 1 && T1 != 1 && T2 != 1, "a partner with tau = 1 divides 0 by 0");
+    constexpr int p0 = PAIR_SLOT[S][0], p1 = PAIR_SLOT[S][1];
+    constexpr bool owe1 = SHARE && SharedBracket<S, 1>::computed && !(BOTH && PAIR_SLOT[S][0] == 0);
+    constexpr bool owe2 = SHARE && SharedBracket<S, 2>::computed;
+    D K1 = D(0.0), K2 = D(0.0);
+    if constexpr (owe1) K1 = (m.upx[p0] * m.upx[p0] + m.upy[p0] * m.upy[p0]) * D(c.hinvcs2);
+    if constexpr (owe2) K2 = (m.upx[p1] * m.upx[p1] + m.upy[p1] * m.upy[p1]) * D(c.hinvcs2);
+    auto relax = [&](const int dir, const D fv, const D gv) {
+        const D fnew = fv - ((div_tau<T0>(dv, fv, c) + div_tau<T1>(dv, fv, c)) + div_tau<T2>(dv, fv, c));
+        const D gnew = gv - ((div_tau<T0>(dv, gv, c) + div_tau<T1>(dv, gv, c)) + div_tau<T2>(dv, gv, c));
+        gt.note_output(fnew);
+        gt.note_output(gnew);
+        o.dst[((S * 2 + 0) * NQ + dir) * o.plane] = fnew.v;
+        o.dst[((S * 2 + 1) * NQ + dir) * o.plane] = gnew.v;
+    };
+    auto ld = [&](const int sk, const int dir) {
+        if constexpr (SHARE) return stash_ld(stash + L::slot(sk, dir));
+        else return D(stash[L::slot(sk, dir)]);
+    };
+    #pragma unroll 1
+    for (int axis = 0; axis < 4; ++axis) {
+        const int d0 = (axis < 2) ? axis + 1 : axis + 3;
+        const D f0 = ld(S * 2 + 0, d0), g0 = ld(S * 2 + 1, d0), f1 = ld(S * 2 + 0, d0 + 2), g1 = ld(S * 2 + 1, d0 + 2);
+        if constexpr (owe1 || owe2) {
+            const AxisSel sel = axis_select(axis);
+            if constexpr (owe1) {
+                const BracketParts bp = bracket_parts(axis_dot(sel, m.upx[p0], m.upy[p0]), c);
+                stash_st(stash + L::slot(SharedBracket<S, 1>::sk, d0), bracket_value<false>(bp, K1));
+                stash_st(stash + L::slot(SharedBracket<S, 1>::sk, d0 + 2), bracket_value<true>(bp, K1));
+            }
+            if constexpr (owe2) {
+                const BracketParts bp = bracket_parts(axis_dot(sel, m.upx[p1], m.upy[p1]), c);
+                stash_st(stash + L::slot(SharedBracket<S, 2>::sk, d0), bracket_value<false>(bp, K2));
+                stash_st(stash + L::slot(SharedBracket<S, 2>::sk, d0 + 2), bracket_value<true>(bp, K2));
+            }
+        }
+        relax(d0, f0, g0);
+        relax(d0 + 2, f1, g1);
+    }
+    const D fr = ld(S * 2 + 0, 0), gr = ld(S * 2 + 1, 0);
+    if constexpr (owe1) stash_st(stash + L::slot(SharedBracket<S, 1>::sk, 0), D(1.0) - K1);
+    if constexpr (owe2) stash_st(stash + L::slot(SharedBracket<S, 2>::sk, 0), D(1.0) - K2);
+    relax(0, fr, gr);
+}
+
 struct NoHook {
     template <int S> __device__ __forceinline__ void at_axis(int) {}
 };
+
+template <class L, bool SHARE, bool CHARGED_EMPTY, class Hook>
+__device__ __forceinline__ void k1_cell_collide(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                                const CellMacro& m, D Ex, D Ey, const K1Out& o, const LbmConsts& c, Hook& hook);
+
+template <bool WRITE_MACRO, class L, bool SHARE, bool CHARGED_EMPTY, class Hook>
+__device__ __forceinline__ void k1_cell_rest(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                             const D (&rl)[3], const D (&mx)[3], const D (&my)[3], const D (&tl)[3], D Ex, D Ey,
+                                             const K1Out& o, const LbmConsts& c, Hook& hook);
 
 // The whole cell.  L: stash layout.  `hook.at_axis<s>(axis)` runs at the top of every iteration of the axis loop of species s
 // (the pool kernel asks for its next tile at one of them).
@@ -200,24 +273,45 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, std::c
                                               D Ex, D Ey, const K1Out& o, const LbmConsts& c, Hook& hook)
 {
     static_assert(!(SHARE && PLBM_K1_UNROLL), "the fully unrolled variant does not hand brackets on");
-    // ---- UpdateMacro ------------------------------------------------------------------------
-    CellMacro m;
-    {
-        D rl[3], mx[3], my[3], tl[3];
-        static_for<3>([&](auto S) {
-            constexpr int s = decltype(S)::value;
-            D f[NQ], g[NQ];
-            #pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                f[i] = D(stash[L::slot(s * 2 + 0, i)]);
-                g[i] = D(stash[L::slot(s * 2 + 1, i)]);
-            }
-            #pragma unroll
-            for (int i = 0; i < NQ; ++i) { gt.note_input(f[i].v); gt.note_input(g[i].v); }
-            rl[s] = sum9(f); mx[s] = moment_x(f); my[s] = moment_y(f); tl[s] = sum9(g);
-        });
-        cell_update_macro(dv, gt, rl, mx, my, tl, Ex, Ey, c, m);
+    // raw sums of the three species (plasma.cpp:352-372)
+    D rl[3], mx[3], my[3], tl[3];
+    static_for<3>([&](auto S) {
+        constexpr int s = decltype(S)::value;
+        D f[NQ], g[NQ];
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            f[i] = D(stash[L::slot(s * 2 + 0, i)]);
+            g[i] = D(stash[L::slot(s * 2 + 1, i)]);
+        }
+        #pragma unroll
+        for (int i = 0; i < NQ; ++i) { gt.note_input(f[i].v); gt.note_input(g[i].v); }
+        rl[s] = sum9(f); mx[s] = moment_x(f); my[s] = moment_y(f); tl[s] = sum9(g);
+    });
+#if PLBM_K1_LIGHT && !PLBM_K1_UNROLL
+    // Two complete copies of the rest of the cell, chosen as soon as the raw densities are known: the general one, and one for
+    // cells whose electrons AND ions are empty (k1_species_empty for both, the full path for the neutrals).  Whole copies, branched
+    // this early, so that the general copy is scheduled exactly like the code without the short path: a branch per species, or
+    // one after UpdateMacro, cost the general path 5-6 % (profiles/r2_k1_sweeps.md).
+    if constexpr (std::is_same_v<Hook, NoHook>) {
+        // (a warp vote: the branch is uniform, so both copies keep their constants in uniform registers; a warp with cells of
+        // both kinds takes the general copy, which is correct for every cell)
+        if (__all_sync(0xffffffffu, rl[0] < D(1e-10) && rl[1] < D(1e-10))) {  // the reference's own test, plasma.cpp:373,393
+            k1_cell_rest<WRITE_MACRO, L, SHARE, true>(dv, gt, stash, rl, mx, my, tl, Ex, Ey, o, c, hook);
+            return;
+        }
     }
+#endif
+    k1_cell_rest<WRITE_MACRO, L, SHARE, false>(dv, gt, stash, rl, mx, my, tl, Ex, Ey, o, c, hook);
+}
+
+// UpdateMacro from the raw sums, then the collisions.  CHARGED_EMPTY: electrons and ions are below the density threshold.
+template <bool WRITE_MACRO, class L, bool SHARE, bool CHARGED_EMPTY, class Hook>
+__device__ __forceinline__ void k1_cell_rest(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                             const D (&rl)[3], const D (&mx)[3], const D (&my)[3], const D (&tl)[3], D Ex, D Ey,
+                                             const K1Out& o, const LbmConsts& c, Hook& hook)
+{
+    CellMacro m;
+    cell_update_macro(dv, gt, rl, mx, my, tl, Ex, Ey, c, m);
     gt.close_macro();
     *o.rho_q = m.rho_q.v;
     if constexpr (WRITE_MACRO) {
@@ -227,12 +321,22 @@ __device__ __forceinline__ void k1_cell_gated(GatedDiv& dv, CellGate& gt, std::c
             o.mo.T[s][o.cidx] = m.T[s].v;   o.mo.rho[s][o.cidx] = m.rho[s].v;
         });
     }
+    k1_cell_collide<L, SHARE, CHARGED_EMPTY>(dv, gt, stash, m, Ex, Ey, o, c, hook);
+}
 
-    // ---- collisions, species by species (small live state per species) -----------------------
-    // Every species needs three equilibrium velocities: its own and those of its two pairs (plasma.cpp:195-304).
+// ---- collisions, species by species (small live state per species) -----------------------
+// Every species needs three equilibrium velocities: its own and those of its two pairs (plasma.cpp:195-304).
+template <class L, bool SHARE, bool CHARGED_EMPTY, class Hook>
+__device__ __forceinline__ void k1_cell_collide(GatedDiv& dv, CellGate& gt, std::conditional_t<SHARE, double*, const double* __restrict__> stash,
+                                                const CellMacro& m, D Ex, D Ey, const K1Out& o, const LbmConsts& c, Hook& hook)
+{
     static_for<3>([&](auto S) {
         constexpr int s = decltype(S)::value;
         constexpr int p0 = PAIR_SLOT[s][0], p1 = PAIR_SLOT[s][1];
+        if constexpr (CHARGED_EMPTY && s < 2) {
+            k1_species_empty<s, L, SHARE, true>(dv, gt, stash, m, o, c);
+            return;
+        }
         const D vx[3] = { m.ux[s], m.upx[p0], m.upx[p1] };
         const D vy[3] = { m.uy[s], m.upy[p0], m.upy[p1] };
         const D u2 = vx[0] * vx[0] + vy[0] * vy[0];                           // collisions.cpp:98-100

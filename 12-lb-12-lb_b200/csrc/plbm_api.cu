@@ -301,7 +301,12 @@ int build_fft(plbm_ctx* c)
     f.k0 = c->slab_k0[c->cfg.rank];
     f.tab.nkl = c->slab_k0[c->cfg.rank + 1] - f.k0;
     if (dev_alloc(c, &f.T1, (size_t)nh * nyl)) return 1;
-    if (R > 1) { if (dev_alloc(c, &f.T2, (size_t)(f.tab.nkl > 0 ? f.tab.nkl : 1) * n0)) return 1; }
+    if (R > 1) {
+        if (dev_alloc(c, &f.T2, (size_t)(f.tab.nkl > 0 ? f.tab.nkl : 1) * n0)) return 1;
+        if (dev_alloc(c, &f.p2_flags, (size_t)f.tab.nkl + 2)) return 1;            // poisson_cols_gather_kernel
+        CUDA_TRY(cudaMemset(f.p2_flags, 0, sizeof(unsigned) * ((size_t)f.tab.nkl + 2)));
+        f.p2_epoch = 0;
+    }
     else f.T2 = f.T1;
     f.row = make_fft_plan(n1, c->tw_row);
     f.col = make_fft_plan(n0, c->tw_col);
@@ -638,6 +643,7 @@ void plbm_destroy(plbm_ctx* c)
     cudaFree(c->err_bits); cudaFree(c->iters_dev);
     cudaFree(c->tw_row); cudaFree(c->tw_col); cudaFree(c->sx2); cudaFree(c->sy2);
     if (c->fft.T2 != c->fft.T1) cudaFree(c->fft.T2);
+    cudaFree(c->fft.p2_flags);
     cudaFree(c->fft.T1);
     cudaFree(c->halo_send_lo); cudaFree(c->halo_send_hi); cudaFree(c->halo_recv_lo); cudaFree(c->halo_recv_hi);
     cudaFree(c->phi_below_base); cudaFree(c->phi_above_base);
@@ -1085,6 +1091,15 @@ int plbm_halo_unpack(plbm_ctx* c)
     return 0;
 }
 
+// P2 through peer memory: copier CTAs gather the columns beside the transforms (poisson_cols.cu); PLBM_P2_GATHER=0 selects the
+// kernel whose CTAs load their own columns over NVLink.
+static cudaError_t launch_p2_peer(plbm_ctx* c, cudaStream_t stream)
+{
+    static const bool gather = []() { const char* e = std::getenv("PLBM_P2_GATHER"); return !(e && e[0] == '0'); }();
+    if (gather && c->fft.p2_flags) return launch_poisson_cols_gather(c->fft, stream, c->peer_t1);
+    return launch_poisson_cols(c->fft, stream, &c->peer_t1);
+}
+
 int plbm_poisson_stage(plbm_ctx* c, int stage)
 {
     DevGuard guard__(c);
@@ -1107,7 +1122,7 @@ int plbm_poisson_stage(plbm_ctx* c, int stage)
         return 0;
     case 4:
         if (!c->peers) return fail("plbm_poisson_stage(4): peer memory is not attached (plbm_peer_attach)");
-        CUDA_TRY(launch_poisson_cols(c->fft, c->stream, &c->peer_t1));
+        CUDA_TRY(launch_p2_peer(c, c->stream));
         return 0;
     default: return fail("plbm_poisson_stage: stage %d", stage);
     }
@@ -1327,7 +1342,7 @@ int step_peer_pipelined(plbm_ctx* c, int nsteps, bool want_fields, StageClock& c
         rc = STAGE(ST_PULL, B, (launch_charge_pull(c->pop[c->cur], c->rho_q_next, g, c->consts.q, c->mass, B) != cudaSuccess ? fail("charge pull launch failed") : 0))
           || STAGE(ST_P1, B, (launch_poisson_rows_fwd(c->fft, c->rho_q_next, B) != cudaSuccess ? fail("P1 launch failed") : 0))
           || STAGE(ST_BAR1, B, peer_barrier_on(c, B, 1))
-          || STAGE(ST_P2, B, (launch_poisson_cols(c->fft, B, &c->peer_t1) != cudaSuccess ? fail("P2 launch failed") : 0))
+          || STAGE(ST_P2, B, (launch_p2_peer(c, B) != cudaSuccess ? fail("P2 launch failed") : 0))
           || STAGE(ST_BAR2, B, peer_barrier_on(c, B, 1))
           || STAGE(ST_P3, B, (launch_poisson_rows_inv(c->fft, c->phi_buf[alt], B, c->down_phi_above_base + alt * NX, c->up_phi_below_base + alt * NX) != cudaSuccess
                               ? fail("P3 launch failed") : 0))

@@ -32,12 +32,15 @@ struct PoissonFftDev {
     const double* sx2;   // sin^2(pi*kx/NX) per row index i        (poisson.cpp:391-395)
     const double* sy2;   // sin^2(pi*ky/NY) per column index j
     double norm;         // 1.0 / (NX*NY)                           (poisson.cpp:415)
+    unsigned* p2_flags;  // several slabs: nkl + 2 words of poisson_cols_gather_kernel (claim counters, group flags)
+    unsigned p2_epoch;   // launches of that kernel so far
 };
 
 FftPlan make_fft_plan(int n, const cpx* tw);   // pass schedule for length n (radix schedule of oracle/fft_oracle.c, grouped)
 cudaError_t poisson_fft_configure(const PoissonFftDev& p);   // after row/col plans are set
 cudaError_t launch_poisson_rows_fwd(const PoissonFftDev& p, const double* rho_q, cudaStream_t stream);   // rho_q -> T1
 cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream, const PeerTable* peer = nullptr);   // T2 in place, or every slab's T1 through peer memory
+cudaError_t launch_poisson_cols_gather(PoissonFftDev& p, cudaStream_t stream, const PeerTable& peer);   // the same through peer memory with copier CTAs
 cudaError_t launch_poisson_rows_inv(const PoissonFftDev& p, double* phi, cudaStream_t stream,
                                     double* first_row_copy = nullptr, double* last_row_copy = nullptr);           // T1 -> phi
 cudaError_t launch_efield_periodic(const double* phi, const double* below, const double* above, double* Ex, double* Ey,

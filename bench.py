@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (tuning sweeps only)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the K1 measurement on an all-dense lattice")
     ap.add_argument("--no-extra", action="store_true", help="skip the strong_8192 / weak_4096 configurations")
     ap.add_argument("--weak-sides", default="friendly", choices=["friendly", "literal"],
                     help="weak_4096 lattice sides: 4096/6144/8192/12288 (default) or the literal roundings 4096/5760/8192/11520")
@@ -309,6 +310,10 @@ def main():
         line["strong_8192"] = single_extra(P, args, local_rank, 8192, "8192x8192 strong scaling (BASELINE.json configs[3])", peak)
         line["weak_4096"] = single_extra(P, args, local_rank, 4096, "4096x4096 = 4096^2 cells per GPU, weak scaling (BASELINE.json configs[4])", peak)
 
+    # ---- K1 on a lattice where all three species are dense in every cell -----------------------------------------------------
+    if not args.no_dense:
+        line["roofline"]["dense_lattice"] = dense_k1(sim, nx, peak)
+
     # ---- parity gate: the timed workload against the host checker ---------------------------
     if not args.no_parity:
         line["parity"] = parity_single(sim, nx, args.poisson, args.parity_steps)
@@ -397,6 +402,28 @@ def main():
         raise SystemExit("bench.py: the timed path is NOT bit-identical to the host checker (see the line's parity object)")
 
 
+def dense_k1(sim, nx, peak, steps=12):
+    """K1 with electrons and ions dense in EVERY cell.  In the reference's initial condition (the timed workload) they fill only the
+    central quarter of the lattice (src/plasma.cpp:128-143) and an empty charged species takes K1's short path (k1_species_empty,
+    bit-identical); this is the kernel's figure when no cell can take it: the populations of the central cell copied to all cells."""
+    sim.initialize()
+    f, g = sim.download_state()
+    c = nx // 2
+    for s in (0, 1):
+        f[s][...] = f[s][c, c, :]
+        g[s][...] = g[s][c, c, :]
+    sim.upload_state(f, g)
+    del f, g
+    sim.step(3)
+    seg = sim.step_timed(steps)
+    sim.sync()
+    k1_ms = seg["ms_k1"] / steps
+    achieved = K1_BYTES_PER_UPDATE * nx * nx / (k1_ms * 1e-3) / 1e9
+    return {"what": "electrons and ions dense in every cell (central cell of the reference's initial condition copied everywhere): "
+                    "no cell takes the empty-species path", "steps": steps, "k1_ms_per_launch": k1_ms, "achieved": achieved,
+            "frac": achieved / peak, "ms_per_step": seg["ms_total"] / steps}
+
+
 def single_extra(P, args, device, nx, label, peak):
     """One more lattice on this GPU: 3 untimed + 12 timed steps from the initial condition, device time from the library's events."""
     K, W = 12, 3
@@ -472,7 +499,7 @@ def roofline(nx, cells, achieved, peak, peak_src, k1_ms, share):
                 traffic = rec.get("dram_bytes_per_launch")
         except Exception:
             pass
-    return {"bound": "hbm", "kernel": "k1_fused_kernel<false,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "k1_tma_kernel<false,true>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic,
             "traffic_source": ("committed ncu capture (profiles/k1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch), "
                                "not measured in this run" if traffic is not None else None),
