@@ -306,6 +306,7 @@ int build_fft(plbm_ctx* c)
         if (dev_alloc(c, &f.p2_flags, (size_t)f.tab.nkl + 2)) return 1;            // poisson_cols_gather_kernel
         CUDA_TRY(cudaMemset(f.p2_flags, 0, sizeof(unsigned) * ((size_t)f.tab.nkl + 2)));
         f.p2_epoch = 0;
+        f.p2_per_sm = 0;
     }
     else f.T2 = f.T1;
     f.row = make_fft_plan(n1, c->tw_row);
@@ -1091,11 +1092,14 @@ int plbm_halo_unpack(plbm_ctx* c)
     return 0;
 }
 
-// P2 through peer memory: copier CTAs gather the columns beside the transforms (poisson_cols.cu); PLBM_P2_GATHER=0 selects the
-// kernel whose CTAs load their own columns over NVLink.
+// P2 through peer memory.  From four slabs on, copier CTAs gather the columns beside the transforms (poisson_cols.cu): on 8 B200s
+// 161 vs 200 us at 6144^2 and 235 vs 296 us at 8192^2.  Not with two slabs (half of every column is local and the kernel whose CTAs
+// load their own columns over NVLink is as fast or faster: 131 vs 144 us at 3072^2, 556 vs 537 us at 8192^2 on 2 B200s) and not
+// beyond 8192 (768-thread transforms: 989 vs 887 us at 12288^2 on 8 B200s).  PLBM_P2_GATHER=1 / 0 forces one or the other.
 static cudaError_t launch_p2_peer(plbm_ctx* c, cudaStream_t stream)
 {
-    static const bool gather = []() { const char* e = std::getenv("PLBM_P2_GATHER"); return !(e && e[0] == '0'); }();
+    static const int forced = []() { const char* e = std::getenv("PLBM_P2_GATHER"); return (e && e[0]) ? (e[0] != '0' ? 1 : 0) : -1; }();
+    const bool gather = forced >= 0 ? forced == 1 : (c->cfg.nranks >= 4 && c->fft.col.threads <= 512);
     if (gather && c->fft.p2_flags) return launch_poisson_cols_gather(c->fft, stream, c->peer_t1);
     return launch_poisson_cols(c->fft, stream, &c->peer_t1);
 }

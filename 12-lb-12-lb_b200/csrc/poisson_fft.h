@@ -34,6 +34,7 @@ struct PoissonFftDev {
     double norm;         // 1.0 / (NX*NY)                           (poisson.cpp:415)
     unsigned* p2_flags;  // several slabs: nkl + 2 words of poisson_cols_gather_kernel (claim counters, group flags)
     unsigned p2_epoch;   // launches of that kernel so far
+    int p2_per_sm;       // its CTAs per SM (0: not queried yet)
 };
 
 FftPlan make_fft_plan(int n, const cpx* tw);   // pass schedule for length n (radix schedule of oracle/fft_oracle.c, grouped)

@@ -28,6 +28,9 @@ inline size_t fft_smem_bytes(int n) { return sizeof(cpx) * (size_t)fft_smem_elem
 template <class F>
 inline cudaError_t with_shape(const FftPlan& P, F&& f)
 {
+#ifdef PLBM_FFT_ONE_SHAPE   // development builds: only the shape of power-of-two lengths 2^(4k+1) <= 8192 (e.g. 8192, 512), seconds to compile
+    return f(std::integral_constant<int, 512>{}, std::integral_constant<int, FFT_TAIL_2>{}, std::integral_constant<int, FFT_ODD_NONE>{});
+#else
     auto odd = [&](auto TAIL) {
         if (P.threads > 512) {
             if (P.odd != FFT_ODD_NONE) return f(std::integral_constant<int, 768>{}, TAIL, std::integral_constant<int, FFT_ODD_GENERIC>{});
@@ -47,6 +50,7 @@ inline cudaError_t with_shape(const FftPlan& P, F&& f)
     case FFT_TAIL_2: return odd(std::integral_constant<int, FFT_TAIL_2>{});
     default: return odd(std::integral_constant<int, FFT_TAIL_NONE>{});
     }
+#endif
 }
 
 template <class K>
