@@ -214,6 +214,35 @@ def test_values_at_the_edges_of_the_gate(oracle, plbm):
     _one_step_against_checker(oracle, plbm, f, g, Ex, Ey, "gate edges", steps=2)
 
 
+
+@pytest.mark.gpu
+def test_empty_charged_species_short_path(oracle, plbm):
+    """Cells whose electrons AND ions are below the density threshold take K1's second copy of the cell code (k1_species_empty:
+    f - ((f/tau_0 + f/tau_1) + f/tau_2) per direction), chosen per warp.  Whole warps of such cells, warps that mix them with
+    dense cells, one species empty only, populations that are tiny but not zero (below the threshold with non-zero f and g), zero
+    g beside non-zero f and the reverse, and empty neutrals (the reference divides 0 by 0 there): all bit-identical to the checker."""
+    NX, NY = 320, 12
+    rng = np.random.default_rng(777)
+    f = rng.uniform(0.05, 1.0, size=(3, NY, NX, 9)); g = rng.uniform(0.01, 0.5, size=(3, NY, NX, 9))
+    f[1] *= 1800.0
+    f[2] *= 1e9
+    Ex = rng.normal(0, 1e-3, size=(NY, NX)); Ey = rng.normal(0, 1e-3, size=(NY, NX))
+    for s in (0, 1):                                   # whole warps and whole tiles of exact zeros
+        f[s][:, 0:128] = 0.0; g[s][:, 0:128] = 0.0
+    f[0][:, 128:160] = 0.0; g[0][:, 128:160] = 0.0     # electrons empty only
+    f[1][:, 160:192] = 0.0; g[1][:, 160:192] = 0.0     # ions empty only
+    for s in (0, 1):                                   # below the threshold but not zero, in a warp of their own ...
+        f[s][:, 192:224] *= 1e-14 / (1800.0 if s else 1.0); g[s][:, 192:224] *= 1e-14
+    for s in (0, 1):                                   # ... and patches narrower than a warp among dense cells
+        f[s][:, 230:237] = 0.0; g[s][:, 230:237] = 0.0
+        f[s][3:5, 250:253] *= 1e-20
+    f[0][:, 260:270] = 0.0; f[1][:, 260:270] = 0.0     # zero f, non-zero g
+    g[0][:, 270:280] = 0.0; g[1][:, 270:280] = 0.0     # zero g, non-zero f (dense: the full path)
+    f[2][:, 64:70] = 0.0; g[2][:, 64:70] = 0.0         # empty neutrals inside the all-empty region
+    f[2][:, 290:296] = 0.0                             # and among dense charged species
+    Ex[:, 100:110] = 0.0; Ey[:, 100:110] = 0.0
+    _one_step_against_checker(oracle, plbm, f, g, Ex, Ey, "empty species", steps=3)
+
 @pytest.mark.parametrize("seed", [11, 12, 13])
 def test_random_exponents_everywhere(oracle, plbm, seed):
     """Fuzz: every one of the 54 populations and both field components of every cell gets an independent magnitude from 2^-1074
