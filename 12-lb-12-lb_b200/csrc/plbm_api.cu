@@ -1053,13 +1053,49 @@ int plbm_host_efield(plbm_ctx* c, int bc_type, double* Ex, double* Ey)
     return 0;
 }
 
+// The cut.  K1's time per cell depends on the plasma the cell holds (k1_kernel.cuh: cells whose electrons and ions are empty run
+// at the memory system's pace, dense cells on the FP64 pipe), and LBmethod's lattices start from the reference's initial condition,
+// electrons and ions in the rows NY/4 < y < 3NY/4 only (src/plasma.cpp:128-143).  An equal split of the rows then makes the slabs
+// without plasma wait for the slabs with it at the first barrier of every step (424 of 3548 us at 8192^2 on 4 B200s, 227 of 1910 on 8).
+// The rows of the central block therefore weigh 1 + alpha: cut r is where the weight reaches r/R of the total, rounded to an even
+// row.  alpha = 0.17 from the measured costs per cell at 8192^2 (133.7 ps empty, 184 ps dense, half of a block row dense, 16.7 ps of
+// row passes of the spectral solve); PLBM_SLAB_ALPHA overrides, 0 gives the equal split.  Results do not depend on the cut.
+static double slab_alpha()
+{
+    static const double a = []() {
+        const char* e = std::getenv("PLBM_SLAB_ALPHA");
+        double v = e ? std::atof(e) : 0.17;
+        return (v >= 0.0 && v <= 4.0) ? v : 0.0;
+    }();
+    return a;
+}
+static int slab_cut(int NY, int r, int R)
+{
+    if (r <= 0) return 0;
+    if (r >= R) return NY;
+    const double alpha = slab_alpha();
+    const long long pairs = NY / 2;
+    if (alpha == 0.0) return (int)(2 * ((pairs * r) / R));
+    const double b0 = NY / 4 + 1, b1 = (3 * NY) / 4, wb = (1.0 + alpha) * (b1 - b0);
+    const double t = (NY + alpha * (b1 - b0)) * r / R;
+    const double y = (t <= b0) ? t : (t <= b0 + wb ? b0 + (t - b0) / (1.0 + alpha) : t - alpha * (b1 - b0));
+    long long c = 2 * (long long)(y / 2.0 + 0.5);
+    if (c < 0) c = 0;
+    if (c > NY) c = NY;
+    return (int)c;
+}
+
 int plbm_slab_of(int NY, int rank, int nranks, int* y0, int* ny_local)
 {
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("plbm_slab_of: rank %d of %d", rank, nranks);
     if (nranks == 1) { if (y0) *y0 = 0; if (ny_local) *ny_local = NY; return 0; }
     if (NY % 2) return fail("plbm_slab_of: NY must be even to cut slabs (the spectral solve transforms rows in pairs)");
     const long long pairs = NY / 2;
-    const int a = (int)(2 * ((pairs * rank) / nranks)), b = (int)(2 * ((pairs * (rank + 1)) / nranks));
+    // the weighted cut must leave every slab at least two rows; otherwise (small lattices) the equal split
+    bool weighted = slab_alpha() > 0.0;
+    for (int r = 0; weighted && r < nranks; ++r) if (slab_cut(NY, r + 1, nranks) - slab_cut(NY, r, nranks) < 2) weighted = false;
+    const int a = weighted ? slab_cut(NY, rank, nranks) : (int)(2 * ((pairs * rank) / nranks));
+    const int b = weighted ? slab_cut(NY, rank + 1, nranks) : (int)(2 * ((pairs * (rank + 1)) / nranks));
     if (b - a < 2) return fail("plbm_slab_of: %d rows cannot feed %d slabs", NY, nranks);
     if (y0) *y0 = a;
     if (ny_local) *ny_local = b - a;
@@ -1095,11 +1131,13 @@ int plbm_halo_unpack(plbm_ctx* c)
 // P2 through peer memory.  From four slabs on, copier CTAs gather the columns beside the transforms (poisson_cols.cu): on 8 B200s
 // 161 vs 200 us at 6144^2 and 235 vs 296 us at 8192^2.  Not with two slabs (half of every column is local and the kernel whose CTAs
 // load their own columns over NVLink is as fast or faster: 131 vs 144 us at 3072^2, 556 vs 537 us at 8192^2 on 2 B200s) and not
-// beyond 8192 (768-thread transforms: 989 vs 887 us at 12288^2 on 8 B200s).  PLBM_P2_GATHER=1 / 0 forces one or the other.
+// beyond 8192 (768-thread transforms: 989 vs 887 us at 12288^2 on 8 B200s), nor up to 4096.  PLBM_P2_GATHER=1 / 0 forces one or the other.
 static cudaError_t launch_p2_peer(plbm_ctx* c, cudaStream_t stream)
 {
     static const int forced = []() { const char* e = std::getenv("PLBM_P2_GATHER"); return (e && e[0]) ? (e[0] != '0' ? 1 : 0) : -1; }();
-    const bool gather = forced >= 0 ? forced == 1 : (c->cfg.nranks >= 4 && c->fft.col.threads <= 512);
+    // (copiers pay where a transform CTA fills an SM: lengths above 4096; at 4096 two CTAs share an SM and cover each other's loads:
+    // 114 vs 158 us at 4096^2 on 4 B200s, against 386 vs 423 us at 8192^2)
+    const bool gather = forced >= 0 ? forced == 1 : (c->cfg.nranks >= 4 && c->fft.col.threads > 256 && c->fft.col.threads <= 512);
     if (gather && c->fft.p2_flags) return launch_poisson_cols_gather(c->fft, stream, c->peer_t1);
     return launch_poisson_cols(c->fft, stream, &c->peer_t1);
 }

@@ -174,7 +174,8 @@ int plbm_host_efield(plbm_ctx* ctx, int bc_type, double* Ex, double* Ey);
 
 /* ---------------------------------------------------------------------------------------------
  * Several slabs (one process per GPU).  The lattice is cut along y; the library owns the rule
- * (plbm_slab_of: even-sized, balanced slabs).  The data path has two exchanges per step, which the
+ * (plbm_slab_of: even-sized slabs, balanced by work: the rows of the reference's central block, where its
+ * initial condition puts the plasma, weigh 1.17; PLBM_SLAB_ALPHA=0 in the environment gives equal slabs).  The data path has two exchanges per step, which the
  * host layer performs between these calls (NCCL send/recv and all-to-all in this repo's driver):
  *   plbm_step_local                      K1 on the slab (halo rows must be current)
  *   plbm_halo_pack -> exchange -> plbm_halo_unpack      18 rows of NX doubles per side

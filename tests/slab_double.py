@@ -10,6 +10,8 @@ must equal the single-domain checker bit for bit.
 import contextlib
 import math
 
+import os
+
 import numpy as np
 import torch
 
@@ -21,9 +23,28 @@ DIR_UP = [2, 5, 6]      # cy = +1: leave through the top of the slab
 DIR_DOWN = [4, 7, 8]    # cy = -1
 
 
+def _slab_cut(NY, r, R, alpha):
+    """Python restatement of the library's cut (csrc/plbm_api.cu: slab_cut): the rows of the reference's central block weigh 1 + alpha."""
+    if r <= 0:
+        return 0
+    if r >= R:
+        return NY
+    if alpha == 0.0:
+        return 2 * (((NY // 2) * r) // R)
+    b0, b1 = float(NY // 4 + 1), float((3 * NY) // 4)
+    wb = (1.0 + alpha) * (b1 - b0)
+    t = (NY + alpha * (b1 - b0)) * r / R
+    y = t if t <= b0 else (b0 + (t - b0) / (1.0 + alpha) if t <= b0 + wb else t - alpha * (b1 - b0))
+    return min(max(2 * int(y / 2.0 + 0.5), 0), NY)
+
+
 def slab_rule(NY, rank, nranks):
-    pairs = NY // 2
-    a, b = 2 * ((pairs * rank) // nranks), 2 * ((pairs * (rank + 1)) // nranks)
+    alpha = float(os.environ.get("PLBM_SLAB_ALPHA", "0.17"))
+    if not 0.0 <= alpha <= 4.0:
+        alpha = 0.0
+    if alpha > 0.0 and any(_slab_cut(NY, r + 1, nranks, alpha) - _slab_cut(NY, r, nranks, alpha) < 2 for r in range(nranks)):
+        alpha = 0.0                       # small lattices: the equal split
+    a, b = _slab_cut(NY, rank, nranks, alpha), _slab_cut(NY, rank + 1, nranks, alpha)
     return a, b - a
 
 

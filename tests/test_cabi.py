@@ -68,3 +68,29 @@ def test_product_never_imports_the_oracle():
                 if re.search(r'^\s*(#\s*include|import|from)\b.*\boracle\b', ln):
                     bad.append(f"{p}: {ln.strip()}")
     assert not bad, bad
+
+
+def test_slab_cut_invariants(plbm):
+    """plbm_slab_of (the library owns the cut): slabs are even-sized, contiguous, cover NY, and at least two rows each, for the
+    weighted default (rows of the reference's central block weigh more) on every lattice the benchmark and the tests
+    cut; small lattices fall back to the equal split.  No GPU needed."""
+    lib = plbm.load_library()
+    lib.plbm_slab_of.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    def cut(NY, R):
+        out = []
+        for r in range(R):
+            y0, n = C.c_int(), C.c_int()
+            assert lib.plbm_slab_of(NY, r, R, C.byref(y0), C.byref(n)) == 0
+            out.append((y0.value, n.value))
+        return out
+    for NY in (16, 20, 60, 64, 96, 200, 256, 1536, 2048, 3072, 4096, 6144, 8192, 12288):
+        for R in (2, 3, 4, 8):
+            if NY // 2 < R:
+                continue
+            c = cut(NY, R)
+            assert c[0][0] == 0 and sum(n for _, n in c) == NY
+            assert all(n >= 2 and n % 2 == 0 for _, n in c), (NY, R, c)
+            assert all(c[i][0] + c[i][1] == c[i + 1][0] for i in range(R - 1))
+    assert [n for _, n in cut(8192, 2)] == [4096, 4096]
+    rows = [n for _, n in cut(8192, 8)]
+    assert rows[0] > rows[3] and rows[0] == rows[7]                                            # outer slabs hold more rows
