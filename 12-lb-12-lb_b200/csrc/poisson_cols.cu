@@ -63,10 +63,10 @@ poisson_cols_kernel(cpx* T, const __grid_constant__ FftPlan plan,
 // ---- P2 over peer memory with the gather off the FFT's critical path ------------------------------------------------------------
 // poisson_cols_kernel with peers is one CTA per SM at the long lengths (a column is 100-140 KB of shared memory), and all CTAs of
 // a wave wait for their remote loads together, compute together and store together: at 8 GPUs the kernel takes the SUM of its
-// NVLink time and its arithmetic (286 us at 8192^2 against ~110 us of arithmetic).  Here a few COPIER CTAs (the lowest block
+// NVLink time and its arithmetic (296 us at 8192^2 against ~130 us of arithmetic).  Here a few COPIER CTAs (the lowest block
 // indices, so they are scheduled first and never wait for anybody) pull the slabs' shares of this rank's columns into the
-// contiguous local buffer T2 = [k_local][n0], group after group, and publish a flag per group; the other CTAs claim columns in the
-// same order, wait for the column's flag, transform it out of T2 and write the result straight into the owning slabs' T1 (posted
+// contiguous local buffer T2 = [k_local][n0], group after group, and publish a flag per group; every other CTA owns one column (CTAs
+// start in index order, the order of the gather), waits for its group's flag, transforms the column out of T2 and writes the result straight into the owning slabs' T1 (posted
 // stores).  The transfers then run beside the arithmetic instead of between it.  Same arithmetic per column, bit-identical.
 struct GatherArgs {
     cpx* T2;               // [nkl][n0]
