@@ -313,6 +313,9 @@ def main():
     # ---- K1 on a lattice where all three species are dense in every cell -----------------------------------------------------
     if not args.no_dense:
         line["roofline"]["dense_lattice"] = dense_k1(sim, nx, peak)
+    line["config"]["k1_cell_paths"] = ("K1's time per cell depends on the data: in this workload (the reference's own initial condition) electrons and "
+                                       "ions fill the central quarter of the lattice, and the cells where both are empty take a shorter, bit-identical copy "
+                                       "of the cell code; roofline.frac is the workload's figure, roofline.dense_lattice the figure with every species in every cell")
 
     # ---- parity gate: the timed workload against the host checker ---------------------------
     if not args.no_parity:
