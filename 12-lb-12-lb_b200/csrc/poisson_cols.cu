@@ -157,7 +157,7 @@ static __device__ __noinline__ void copier_tma(const SlabTable& tab, const PeerT
     ld.start_group(ga.group, nkl);
     st = ld;
     int loads = 0, stores = 0;                 // pieces issued so far
-    int pend_g[16], pend_last[16], head = 0, tail = 0;      // groups whose stores are all issued, waiting for their completion
+    int pend_g[16] = { 0 }, pend_last[16] = { 0 }, head = 0, tail = 0;      // groups whose stores are all issued, waiting for their completion
     auto publish_through = [&](int last_complete) {
         bool any = false;
         while (head != tail && pend_last[head & 15] <= last_complete) {
@@ -325,16 +325,19 @@ cudaError_t launch_poisson_cols(const PoissonFftDev& p, cudaStream_t stream, con
 cudaError_t launch_poisson_cols_gather(PoissonFftDev& p, cudaStream_t stream, const PeerTable& peer)
 {
     if (p.tab.nkl <= 0) return cudaSuccess;
-    static int sms = 0, want_copiers = 0;
-    if (!sms) {
+    // (read once; thread-safe: with PLBM_DEVICES=N one host thread per device comes through here)
+    struct Setup { int sms, want_copiers; cudaError_t err; };
+    static const Setup setup = []() {
+        Setup u = { 0, 24, cudaSuccess };
         int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        const char* env = std::getenv("PLBM_P2_COPIERS");
-        want_copiers = env ? std::atoi(env) : 24;
-        if (want_copiers < 1) want_copiers = 1;
-    }
+        u.err = cudaGetDevice(&dev);
+        if (u.err == cudaSuccess) u.err = cudaDeviceGetAttribute(&u.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (const char* env = std::getenv("PLBM_P2_COPIERS")) u.want_copiers = std::atoi(env);
+        if (u.want_copiers < 1) u.want_copiers = 1;
+        return u;
+    }();
+    if (setup.err != cudaSuccess || setup.sms < 2) return setup.err != cudaSuccess ? setup.err : cudaErrorInvalidDevice;
+    const int sms = setup.sms, want_copiers = setup.want_copiers;
     GatherArgs ga;
     ga.T2 = p.T2;
     ga.flags = p.p2_flags;
